@@ -1,0 +1,12 @@
+"""B200-native block preconditioner for the two-phase MAC-grid Stokes system.
+
+The directory name follows the project (`mp-block-preconditioners_b200`); import it through the
+`mp_block_preconditioners_b200` alias package at the repo root.  Modules mirror the reference's flat
+layout: preconditioner.py, solve.py, apply.py, utils.py.
+"""
+from ._cabi import MpbpError, SIDE_LEFT, SIDE_RIGHT  # noqa: F401
+from .preconditioner import (ApproxSchurOperator, MultiphaseBlockPreconditioner, Plan, SubSolver,  # noqa: F401
+                             SystemOperator, thn, ths)
+from .solve import (Jacobi, fgmres, gmres, main, print_true_res_norm, solve_with_approx_schur_pc,  # noqa: F401
+                    solve_without_pc)
+from .utils import fill_sol_and_RHS_vecs, max_norm, print_norms, weighted_L1, weighted_L2  # noqa: F401

@@ -1,0 +1,224 @@
+// Krylov vector kernels (fp64): deterministic two-stage reductions (warp shuffle -> block -> last
+// block sums the per-block partials in a fixed order) and streaming axpy-type updates.
+// Replaces np.dot / np.linalg.norm / vector updates inside the reference's Krylov solvers
+// (solve.py:167-168, :285; utils.py:7-17).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mpbp {
+
+constexpr int kRedThreads = 256;
+constexpr int kMaxRedBlocks = 1184;  // 148 SMs x 8
+constexpr int kMaxMulti = 8;         // vectors handled per multi-dot / multi-axpy launch
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// sums `v` over the block; result valid in thread 0. smem: kRedThreads/32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* smem) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = (lane < kRedThreads / 32) ? smem[lane] : 0.0;
+    v = warp_sum(v);
+  }
+  return v;
+}
+__device__ __forceinline__ double block_max(double v, double* smem) {
+  v = warp_max(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = (lane < kRedThreads / 32) ? smem[lane] : 0.0;
+    v = warp_max(v);
+  }
+  return v;
+}
+
+// last-arriving block detection
+__device__ __forceinline__ bool last_block(unsigned int* counter) {
+  __shared__ bool is_last;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  return is_last;
+}
+
+// out[k] = sum_i V_k[i] * w[i], k < NV (V_k = V + k*ld).  partial: gridDim.x * NV doubles.
+// post: 0 none, 1 sqrt (nrm2 on one rank)
+template <int NV>
+__global__ void __launch_bounds__(kRedThreads) k_multi_dot(const double* __restrict__ V, size_t ld,
+                                                           const double* __restrict__ w, size_t len,
+                                                           double* __restrict__ partial, unsigned int* counter,
+                                                           double* __restrict__ out, int post) {
+  __shared__ double smem[kRedThreads / 32];
+  double acc[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+    const double wi = w[i];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = fma(V[k * ld + i], wi, acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double s = block_sum(acc[k], smem);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * NV + k] = s;
+  }
+  if (last_block(counter)) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double s = 0.0;
+      for (int bI = threadIdx.x; bI < (int)gridDim.x; bI += blockDim.x) s += partial[(size_t)bI * NV + k];
+      s = block_sum(s, smem);
+      if (threadIdx.x == 0) out[k] = (post == 1) ? sqrt(s) : s;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+  }
+}
+
+// out[0] = sum x  (used for the mean removal, solve.py:260-264)
+__global__ void __launch_bounds__(kRedThreads) k_sum(const double* __restrict__ x, size_t len,
+                                                     double* __restrict__ partial, unsigned int* counter,
+                                                     double* __restrict__ out) {
+  __shared__ double smem[kRedThreads / 32];
+  double acc = 0.0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) acc += x[i];
+  const double s = block_sum(acc, smem);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  if (last_block(counter)) {
+    double t = 0.0;
+    for (int bI = threadIdx.x; bI < (int)gridDim.x; bI += blockDim.x) t += partial[bI];
+    t = block_sum(t, smem);
+    if (threadIdx.x == 0) {
+      out[0] = t;
+      *counter = 0u;
+    }
+  }
+}
+
+// weighted_L1 / weighted_L2 / max_norm of a-b (utils.py:7-17): out = {sum|q|, sum q^2, max|q|} (unweighted)
+__global__ void __launch_bounds__(kRedThreads) k_diffnorms(const double* __restrict__ a, const double* __restrict__ b,
+                                                           size_t len, double* __restrict__ partial,
+                                                           unsigned int* counter, double* __restrict__ out) {
+  __shared__ double smem[kRedThreads / 32];
+  double s1 = 0.0, s2 = 0.0, mx = 0.0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+    const double q = fabs(a[i] - b[i]);
+    s1 += q;
+    s2 = fma(q, q, s2);
+    mx = fmax(mx, q);
+  }
+  s1 = block_sum(s1, smem);
+  s2 = block_sum(s2, smem);
+  mx = block_max(mx, smem);
+  if (threadIdx.x == 0) {
+    partial[3 * blockIdx.x] = s1;
+    partial[3 * blockIdx.x + 1] = s2;
+    partial[3 * blockIdx.x + 2] = mx;
+  }
+  if (last_block(counter)) {
+    double t1 = 0.0, t2 = 0.0, tm = 0.0;
+    for (int bI = threadIdx.x; bI < (int)gridDim.x; bI += blockDim.x) {
+      t1 += partial[3 * bI];
+      t2 += partial[3 * bI + 1];
+      tm = fmax(tm, partial[3 * bI + 2]);
+    }
+    t1 = block_sum(t1, smem);
+    t2 = block_sum(t2, smem);
+    tm = block_max(tm, smem);
+    if (threadIdx.x == 0) {
+      out[0] = t1;
+      out[1] = t2;
+      out[2] = tm;
+      *counter = 0u;
+    }
+  }
+}
+
+__global__ void k_sqrt_inplace(double* v, int nv) {
+  const int i = threadIdx.x;
+  if (i < nv) v[i] = sqrt(v[i]);
+}
+
+struct Alphas {
+  double a[kMaxMulti];
+};
+
+// y += sum_k alpha[k] * V_k  (alpha by value)
+template <int NV>
+__global__ void __launch_bounds__(256) k_multi_axpy(const double* __restrict__ V, size_t ld, Alphas al,
+                                                    double* __restrict__ y, size_t len) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+    double acc = y[i];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc = fma(al.a[k], V[k * ld + i], acc);
+    y[i] = acc;
+  }
+}
+
+// y += sign * (*alpha_dev) * x   (alpha stays on the device: no host round trip inside Gram-Schmidt)
+__global__ void __launch_bounds__(256) k_axpy_dev(const double* __restrict__ alpha_dev, double sign,
+                                                  const double* __restrict__ x, double* __restrict__ y, size_t len) {
+  const double al = sign * alpha_dev[0];
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) y[i] = fma(al, x[i], y[i]);
+}
+
+// y = x * s  with s = *s_dev or 1 / *s_dev (skipped when the scalar is 0: GMRES breakdown)
+__global__ void __launch_bounds__(256) k_scale_dev(const double* s_dev, int reciprocal, const double* x, double* y,
+                                                   size_t len) {
+  double s = s_dev[0];
+  if (reciprocal) s = (s != 0.0) ? 1.0 / s : 1.0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) y[i] = x[i] * s;
+}
+
+// z = a*x + b*y (any of z may alias x or y)
+__global__ void __launch_bounds__(256) k_axpby(double a, const double* x, double b, const double* y, double* z,
+                                               size_t len) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) z[i] = a * x[i] + b * y[i];
+}
+
+// x -= (*sum_dev) * inv_count   (mean removal)
+__global__ void __launch_bounds__(256) k_shift_dev(const double* __restrict__ sum_dev, double inv_count,
+                                                   double* __restrict__ x, size_t len) {
+  const double m = sum_dev[0] * inv_count;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) x[i] -= m;
+}
+
+// Chebyshev update: d = a*d + b*z ; x += d
+__global__ void __launch_bounds__(256) k_cheb_update(double a, double b, const double* __restrict__ z,
+                                                     double* __restrict__ d, double* __restrict__ x, size_t len) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+    const double dn = a * d[i] + b * z[i];
+    d[i] = dn;
+    x[i] += dn;
+  }
+}
+
+}  // namespace mpbp

@@ -1,0 +1,1413 @@
+// libmpbp.so -- host side of the C ABI declared in include/mpbp.h: plan (multigrid hierarchy,
+// workspace, slab decomposition), sub-solvers, the block preconditioner apply (solve.py:257-277)
+// and the Krylov drivers (scipy gmres / pyamg fgmres semantics).  All arithmetic on vectors runs in
+// the CUDA kernels of stencil.cuh / blas1.cuh; there is no CPU fallback.
+#include "../../include/mpbp.h"
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "blas1.cuh"
+#include "stencil.cuh"
+
+using namespace mpbp;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return set_err((int)e_ > 0 ? (int)e_ : 999, "%s:%d CUDA error %d: %s", __FILE__, __LINE__, (int)e_, \
+                     cudaGetErrorString(e_));                                                            \
+  } while (0)
+#define NC(call)                                                                                              \
+  do {                                                                                                        \
+    ncclResult_t e_ = (call);                                                                                 \
+    if (e_ != ncclSuccess)                                                                                    \
+      return set_err(1000 + (int)e_, "%s:%d NCCL error %d: %s", __FILE__, __LINE__, (int)e_, ncclGetErrorString(e_)); \
+  } while (0)
+#define RET(call)          \
+  do {                     \
+    int r_ = (call);       \
+    if (r_ != 0) return r_; \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+struct Level {
+  int n = 0, rows = 0, row0 = 0;
+  bool dist = false;  // slab-distributed over ranks (needs halo exchange); false = whole grid on this rank
+  Geo geo{};
+  Phys ph{};
+  double* th = nullptr;    // padded theta: (rows+2) x n
+  double* halo = nullptr;  // [2][5][n] receive rows (dist only)
+  double *bF = nullptr, *xF = nullptr, *tF = nullptr, *rF = nullptr;  // 4*rows*n each
+  double *bP = nullptr, *xP = nullptr, *tP = nullptr, *rP = nullptr;  // rows*n each
+  double *gF = nullptr, *gP = nullptr;  // restricted slab before the all-gather (first replicated level only)
+  size_t fs() const { return (size_t)rows * n; }
+};
+
+struct Bump {
+  char* base = nullptr;
+  size_t off = 0, cap = 0;
+  bool dry = true;
+  template <class T>
+  T* take(size_t count) {
+    off = (off + 255) & ~size_t(255);
+    T* p = dry ? nullptr : reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+struct mpbp_plan {
+  mpbp_config cfg{};
+  int nranks = 1, rank = 0;
+  ncclComm_t comm = nullptr;
+  std::vector<Level> lev;
+  int first_repl = -1;  // index of the first replicated level when nranks > 1 (else -1)
+  // coarsest dense (pseudo-)inverses, column-major on the device
+  double *FinvT = nullptr, *PinvT = nullptr;
+  int mF = 0, mP = 0;
+  // tables for the analytic mass term (level 0)
+  double *sxf = nullptr, *sxc = nullptr, *syf = nullptr, *syc = nullptr;
+  // level-0 scratch
+  double *w = nullptr, *g = nullptr, *t2 = nullptr;                 // 4N
+  double *rinF = nullptr, *zF = nullptr, *dvF = nullptr;            // 4N
+  double *rhs = nullptr, *xa = nullptr, *xb = nullptr;              // N
+  double *rinP = nullptr, *zP = nullptr, *dvP = nullptr;            // N
+  // reductions
+  double* partial = nullptr;
+  unsigned int* counter = nullptr;
+  double* scal = nullptr;  // device scalars
+  double* hscal = nullptr; // pinned host mirror
+  int red_blocks = 592;
+  // memory ownership
+  void* owned = nullptr;
+  void* kry_owned = nullptr;
+  size_t kry_owned_bytes = 0;
+  double* hostbuf_dev[2] = {nullptr, nullptr};  // staging for the *_host entry points
+  long long launches = 0;
+  cudaStream_t st = nullptr;
+};
+
+static constexpr int kScal = 1024;
+
+static int build_levels_shape(const mpbp_config& c, std::vector<Level>& lev, int& first_repl) {
+  lev.clear();
+  first_repl = -1;
+  const int P = c.nranks;
+  int n = c.n;
+  if (P > 1 && (n % P != 0)) return set_err(MPBP_E_ARG, "n=%d not divisible by nranks=%d", n, P);
+  bool dist = P > 1;
+  int rows = n / P;
+  while (true) {
+    Level L;
+    L.n = n;
+    L.dist = dist;
+    L.rows = dist ? rows : n;
+    L.row0 = dist ? c.rank * rows : 0;
+    lev.push_back(L);
+    const bool last = c.operators_only || (n <= c.n_coarse) || (n % 2) || (n / 2 < 2);
+    if (last) break;
+    if (dist) {
+      // the next level stays distributed only if it keeps >= 2 rows per rank, is not the coarsest
+      // level (the dense solve is replicated) and this level's slab can be restricted locally
+      if (rows % 2) return set_err(MPBP_E_ARG, "slab of %d rows at level n=%d cannot be coarsened", rows, n);
+      const int nn = n / 2, nrows = rows / 2;
+      const bool next_last = (nn <= c.n_coarse) || (nn % 2) || (nn / 2 < 2);
+      if (nrows < 2 || (nrows % 2) || next_last) {
+        dist = false;
+        first_repl = (int)lev.size();
+      }
+      rows = nrows;
+    }
+    n /= 2;
+  }
+  if (!c.operators_only && lev.back().n > 16)
+    return set_err(MPBP_E_ARG, "n=%d coarsens only down to %d (> 16): n needs more factors of 2", c.n, lev.back().n);
+  if (P > 1 && lev.back().dist && !c.operators_only)
+    return set_err(MPBP_E_UNSUPPORTED, "nranks>1 needs at least one coarsening step (n=%d, n_coarse=%d)", c.n, c.n_coarse);
+  if ((int)lev.size() > 1 && (c.nu1 < 1 || c.nu2 < 0)) return set_err(MPBP_E_ARG, "need nu1>=1, nu2>=0");
+  return 0;
+}
+
+static void carve(mpbp_plan* p, Bump& B) {
+  const int L = (int)p->lev.size();
+  for (int l = 0; l < L; ++l) {
+    Level& v = p->lev[l];
+    const size_t fs = v.fs();
+    v.th = B.take<double>((size_t)(v.rows + 2) * v.n);
+    v.halo = v.dist ? B.take<double>((size_t)2 * 5 * v.n) : nullptr;
+    v.tF = B.take<double>(4 * fs);
+    v.rF = B.take<double>(4 * fs);
+    v.tP = B.take<double>(fs);
+    v.rP = B.take<double>(fs);
+    if (l > 0) {
+      v.bF = B.take<double>(4 * fs);
+      v.xF = B.take<double>(4 * fs);
+      v.bP = B.take<double>(fs);
+      v.xP = B.take<double>(fs);
+    }
+    if (l == p->first_repl) {
+      const Level& f = p->lev[l - 1];
+      v.gF = B.take<double>(4 * (f.fs() / 4));
+      v.gP = B.take<double>(f.fs() / 4);
+    }
+  }
+  const size_t fs0 = p->lev[0].fs();
+  p->w = B.take<double>(4 * fs0);
+  p->g = B.take<double>(4 * fs0);
+  p->t2 = B.take<double>(4 * fs0);
+  p->rinF = B.take<double>(4 * fs0);
+  p->zF = B.take<double>(4 * fs0);
+  p->dvF = B.take<double>(4 * fs0);
+  p->rhs = B.take<double>(fs0);
+  p->xa = B.take<double>(fs0);
+  p->xb = B.take<double>(fs0);
+  p->rinP = B.take<double>(fs0);
+  p->zP = B.take<double>(fs0);
+  p->dvP = B.take<double>(fs0);
+  const Level& c = p->lev.back();
+  p->mF = p->cfg.operators_only ? 0 : 4 * c.n * c.n;
+  p->mP = p->cfg.operators_only ? 0 : c.n * c.n;
+  p->FinvT = B.take<double>((size_t)p->mF * p->mF);
+  p->PinvT = B.take<double>((size_t)p->mP * p->mP);
+  const int n0 = p->lev[0].n;
+  p->sxf = B.take<double>(n0);
+  p->sxc = B.take<double>(n0);
+  p->syf = B.take<double>(n0);
+  p->syc = B.take<double>(n0);
+  p->partial = B.take<double>((size_t)kMaxRedBlocks * kMaxMulti);
+  p->counter = B.take<unsigned int>(64);
+  p->scal = B.take<double>(kScal);
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------
+static inline dim3 stencil_grid(const Level& v) {
+  return dim3((unsigned)((v.n + kWarpCols * kBlockWarps - 1) / (kWarpCols * kBlockWarps)),
+              (unsigned)((v.rows + v.geo.rs - 1) / v.geo.rs));
+}
+static inline int ew_blocks(size_t len) { return (int)std::min<size_t>((len + 255) / 256, 148 * 16); }
+
+#define LAUNCH_CHECK(p)    \
+  do {                     \
+    (p)->launches++;       \
+    CU(cudaGetLastError()); \
+  } while (0)
+
+// neighbour rows of a distributed level's vector (nf fields, field stride fs) into lev.halo
+static int halo_exchange(mpbp_plan* p, Level& v, const double* x, int nf, size_t fs) {
+  const int P = p->nranks, prev = (p->rank + P - 1) % P, next = (p->rank + 1) % P;
+  const size_t n = v.n;
+  double* top = v.halo;
+  double* bot = v.halo + 5 * n;
+  NC(ncclGroupStart());
+  for (int k = 0; k < nf; ++k) {
+    // order matters when prev == next (2 ranks): my last row is the peer's top halo
+    NC(ncclSend(x + k * fs + (size_t)(v.rows - 1) * n, n, ncclDouble, next, p->comm, p->st));
+    NC(ncclSend(x + k * fs, n, ncclDouble, prev, p->comm, p->st));
+    NC(ncclRecv(top + k * n, n, ncclDouble, prev, p->comm, p->st));
+    NC(ncclRecv(bot + k * n, n, ncclDouble, next, p->comm, p->st));
+  }
+  NC(ncclGroupEnd());
+  return 0;
+}
+
+// view of a level vector for stencil kernels (performs the halo exchange when distributed)
+static int make_view(mpbp_plan* p, Level& v, const double* x, int nf, VecIn& out) {
+  const size_t fs = v.fs();
+  out.x = x;
+  out.fs = fs;
+  if (v.dist) {
+    RET(halo_exchange(p, v, x, nf, fs));
+    out.top = v.halo;
+    out.bot = v.halo + 5 * (size_t)v.n;
+    out.hs = v.n;
+  } else {
+    out.top = x + (size_t)(v.rows - 1) * v.n;
+    out.bot = x;
+    out.hs = fs;
+  }
+  return 0;
+}
+
+static int allreduce_scal(mpbp_plan* p, double* dev, int count) {
+  if (p->nranks > 1) NC(ncclAllReduce(dev, dev, count, ncclDouble, ncclSum, p->comm, p->st));
+  return 0;
+}
+
+// ---- operator launches -----------------------------------------------------------------------
+static int op_stokes(mpbp_plan* p, int l, int mode, bool with_p, const double* x, const double* b, double* y,
+                     double omega) {
+  Level& v = p->lev[l];
+  VecIn in;
+  RET(make_view(p, v, x, with_p ? 5 : 4, in));
+  const dim3 grid = stencil_grid(v), block(kBlockThreads);
+  if (with_p)
+    k_stokes<0, true><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega);
+  else if (mode == 0)
+    k_stokes<0, false><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega);
+  else if (mode == 1)
+    k_stokes<1, false><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega);
+  else
+    k_stokes<2, false><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega);
+  LAUNCH_CHECK(p);
+  return 0;
+}
+static int op_jacobi0_F(mpbp_plan* p, int l, const double* b, double* y, double omega) {
+  Level& v = p->lev[l];
+  k_jacobi0_F<<<stencil_grid(v), kBlockThreads, 0, p->st>>>(v.th, b, y, v.fs(), v.geo, v.ph, omega);
+  LAUNCH_CHECK(p);
+  return 0;
+}
+static int op_poisson(mpbp_plan* p, int l, int mode, const double* x, const double* b, double* y, double omega) {
+  Level& v = p->lev[l];
+  VecIn in{};
+  if (mode != 3) RET(make_view(p, v, x, 1, in));
+  const dim3 grid = stencil_grid(v), block(kBlockThreads);
+  switch (mode) {
+    case 0: k_poisson<0><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega); break;
+    case 1: k_poisson<1><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega); break;
+    case 2: k_poisson<2><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega); break;
+    default: k_poisson<3><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega); break;
+  }
+  LAUNCH_CHECK(p);
+  return 0;
+}
+// r = scale * D w + add
+static int op_div(mpbp_plan* p, int l, const double* w, const double* add, double* r, double scale) {
+  Level& v = p->lev[l];
+  VecIn in;
+  RET(make_view(p, v, w, 4, in));
+  Phys ph = v.ph;
+  ph.inv_h *= scale;
+  k_div<<<stencil_grid(v), kBlockThreads, 0, p->st>>>(in, v.th, add, r, v.geo, ph);
+  LAUNCH_CHECK(p);
+  return 0;
+}
+static int op_grad(mpbp_plan* p, int l, const double* pr, double* y) {
+  Level& v = p->lev[l];
+  VecIn in;
+  RET(make_view(p, v, pr, 1, in));
+  k_grad<<<stencil_grid(v), kBlockThreads, 0, p->st>>>(in, v.th, y, v.fs(), v.geo, v.ph);
+  LAUNCH_CHECK(p);
+  return 0;
+}
+static int op_dense(mpbp_plan* p, const double* Mt, const double* x, double* y, int m) {
+  k_dense_matvec<<<1, 256, m * sizeof(double), p->st>>>(Mt, x, y, m);
+  LAUNCH_CHECK(p);
+  return 0;
+}
+
+// ---- grid transfers ---------------------------------------------------------------------------
+// b_{l+1} = R r_l
+static int op_restrict(mpbp_plan* p, int l, bool isF, const double* r) {
+  Level& f = p->lev[l];
+  Level& c = p->lev[l + 1];
+  const bool gather = (l + 1 == p->first_repl);
+  const int rows_c = f.rows / 2, nc = f.n / 2;
+  const dim3 block(128), grid((nc + 127) / 128, rows_c);
+  if (isF) {
+    VecIn in;
+    RET(make_view(p, f, r, 4, in));
+    double* dst = gather ? c.gF : c.bF;
+    k_restrict_F<<<grid, block, 0, p->st>>>(in, dst, f.n, f.rows);
+    LAUNCH_CHECK(p);
+    if (gather) {
+      const size_t cnt = (size_t)rows_c * nc;
+      NC(ncclGroupStart());
+      for (int k = 0; k < 4; ++k)
+        NC(ncclAllGather(dst + k * cnt, c.bF + k * c.fs(), cnt, ncclDouble, p->comm, p->st));
+      NC(ncclGroupEnd());
+    }
+  } else {
+    double* dst = gather ? c.gP : c.bP;
+    k_restrict_P<<<grid, block, 0, p->st>>>(r, dst, f.n, f.rows);
+    LAUNCH_CHECK(p);
+    if (gather) NC(ncclAllGather(dst, c.bP, (size_t)rows_c * nc, ncclDouble, p->comm, p->st));
+  }
+  return 0;
+}
+// x_l += P x_{l+1}
+static int op_prolong_add(mpbp_plan* p, int l, bool isF, double* x) {
+  Level& f = p->lev[l];
+  Level& c = p->lev[l + 1];
+  const dim3 block(128), grid((f.n + 127) / 128, f.rows);
+  if (isF) {
+    VecIn in;
+    if (l + 1 == p->first_repl) {
+      // coarse level is replicated: address this rank's rows inside the full coarse grid
+      const int R0 = f.row0 / 2, rows_c = f.rows / 2, nc = c.n;
+      in.x = c.xF + (size_t)R0 * nc;
+      in.fs = in.hs = c.fs();
+      in.top = c.xF + (size_t)((R0 + nc - 1) % nc) * nc;
+      in.bot = c.xF + (size_t)((R0 + rows_c) % nc) * nc;
+    } else {
+      RET(make_view(p, c, c.xF, 4, in));
+    }
+    k_prolong_add_F<<<grid, block, 0, p->st>>>(in, x, f.n, f.rows);
+  } else {
+    const double* xc = c.xP;
+    if (l + 1 == p->first_repl) xc += (size_t)(f.row0 / 2) * c.n;
+    k_prolong_add_P<<<grid, block, 0, p->st>>>(xc, x, f.n, f.rows);
+  }
+  LAUNCH_CHECK(p);
+  return 0;
+}
+
+// ---- vector helpers ---------------------------------------------------------------------------
+static int v_axpby(mpbp_plan* p, double a, const double* x, double b, const double* y, double* z, size_t len) {
+  k_axpby<<<ew_blocks(len), 256, 0, p->st>>>(a, x, b, y, z, len);
+  LAUNCH_CHECK(p);
+  return 0;
+}
+static int v_copy(mpbp_plan* p, const double* x, double* y, size_t len) {
+  CU(cudaMemcpyAsync(y, x, len * sizeof(double), cudaMemcpyDeviceToDevice, p->st));
+  return 0;
+}
+// out_dev[k] = <V_k, w> summed over ranks; post_sqrt applies sqrt to each result
+static int v_multi_dot(mpbp_plan* p, const double* V, size_t ld, int nvec, const double* w, size_t len,
+                       double* out_dev, bool post_sqrt) {
+  const int blocks = (int)std::min<size_t>((len + kRedThreads - 1) / kRedThreads, (size_t)p->red_blocks);
+  const int post = (post_sqrt && p->nranks == 1) ? 1 : 0;
+  for (int k0 = 0; k0 < nvec; k0 += kMaxMulti) {
+    const int nv = std::min(kMaxMulti, nvec - k0);
+    const double* Vk = V + (size_t)k0 * ld;
+    double* o = out_dev + k0;
+    switch (nv) {
+      case 1: k_multi_dot<1><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post); break;
+      case 2: k_multi_dot<2><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post); break;
+      case 3: k_multi_dot<3><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post); break;
+      case 4: k_multi_dot<4><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post); break;
+      case 5: k_multi_dot<5><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post); break;
+      case 6: k_multi_dot<6><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post); break;
+      case 7: k_multi_dot<7><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post); break;
+      default: k_multi_dot<8><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post); break;
+    }
+    LAUNCH_CHECK(p);
+  }
+  if (p->nranks > 1) {
+    RET(allreduce_scal(p, out_dev, nvec));
+    if (post_sqrt) {
+      k_sqrt_inplace<<<1, 256, 0, p->st>>>(out_dev, nvec);
+      LAUNCH_CHECK(p);
+    }
+  }
+  return 0;
+}
+static int v_dot(mpbp_plan* p, const double* x, const double* y, size_t len, double* out_dev) {
+  return v_multi_dot(p, x, 0, 1, y, len, out_dev, false);
+}
+static int v_nrm2(mpbp_plan* p, const double* x, size_t len, double* out_dev) {
+  return v_multi_dot(p, x, 0, 1, x, len, out_dev, true);
+}
+static int v_multi_axpy(mpbp_plan* p, const double* V, size_t ld, int nvec, const double* alpha_host, double* y,
+                        size_t len) {
+  for (int k0 = 0; k0 < nvec; k0 += kMaxMulti) {
+    const int nv = std::min(kMaxMulti, nvec - k0);
+    Alphas al{};
+    for (int k = 0; k < nv; ++k) al.a[k] = alpha_host[k0 + k];
+    const double* Vk = V + (size_t)k0 * ld;
+    const int blocks = ew_blocks(len);
+    switch (nv) {
+      case 1: k_multi_axpy<1><<<blocks, 256, 0, p->st>>>(Vk, ld, al, y, len); break;
+      case 2: k_multi_axpy<2><<<blocks, 256, 0, p->st>>>(Vk, ld, al, y, len); break;
+      case 3: k_multi_axpy<3><<<blocks, 256, 0, p->st>>>(Vk, ld, al, y, len); break;
+      case 4: k_multi_axpy<4><<<blocks, 256, 0, p->st>>>(Vk, ld, al, y, len); break;
+      case 5: k_multi_axpy<5><<<blocks, 256, 0, p->st>>>(Vk, ld, al, y, len); break;
+      case 6: k_multi_axpy<6><<<blocks, 256, 0, p->st>>>(Vk, ld, al, y, len); break;
+      case 7: k_multi_axpy<7><<<blocks, 256, 0, p->st>>>(Vk, ld, al, y, len); break;
+      default: k_multi_axpy<8><<<blocks, 256, 0, p->st>>>(Vk, ld, al, y, len); break;
+    }
+    LAUNCH_CHECK(p);
+  }
+  return 0;
+}
+// fetch `count` device scalars to the pinned host mirror (synchronises the stream)
+static int fetch_scal(mpbp_plan* p, const double* dev, int count, double* host) {
+  CU(cudaMemcpyAsync(host, dev, count * sizeof(double), cudaMemcpyDeviceToHost, p->st));
+  CU(cudaStreamSynchronize(p->st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sub-solvers
+// ---------------------------------------------------------------------------------------------
+// `sweeps` damped Jacobi sweeps starting from x (in place); tmp is a same-size scratch buffer
+static int jacobi_sweeps(mpbp_plan* p, int l, bool isF, const double* b, double* x, double* tmp, int sweeps,
+                         double omega) {
+  Level& v = p->lev[l];
+  const size_t len = (isF ? 4 : 1) * v.fs();
+  double* cur = x;
+  double* oth = tmp;
+  for (int s = 0; s < sweeps; ++s) {
+    if (isF) RET(op_stokes(p, l, 2, false, cur, b, oth, omega));
+    else RET(op_poisson(p, l, 2, cur, b, oth, omega));
+    std::swap(cur, oth);
+  }
+  if (cur != x) RET(v_copy(p, cur, x, len));
+  return 0;
+}
+
+// x = V b: one V(nu1,nu2) cycle from a zero guess.  x must not alias the level's t/r buffers.
+static int vcycle(mpbp_plan* p, int l, bool isF, const double* b, double* x) {
+  const mpbp_config& c = p->cfg;
+  if (c.operators_only) return set_err(MPBP_E_STATE, "plan was created with operators_only");
+  Level& v = p->lev[l];
+  const int L = (int)p->lev.size();
+  if (l == L - 1) {
+    // coarsest level: dense inverse (F) / pseudo-inverse (GtG)
+    return isF ? op_dense(p, p->FinvT, b, x, p->mF) : op_dense(p, p->PinvT, b, x, p->mP);
+  }
+  double* t = isF ? v.tF : v.tP;
+  double* r = isF ? v.rF : v.rP;
+  const int S = (c.nu1 - 1) + c.nu2;
+  double* cur = (S % 2 == 0) ? x : t;
+  double* oth = (cur == x) ? t : x;
+  if (isF) RET(op_jacobi0_F(p, l, b, cur, c.omega));
+  else RET(op_poisson(p, l, 3, nullptr, b, cur, c.omega));
+  for (int s = 1; s < c.nu1; ++s) {
+    if (isF) RET(op_stokes(p, l, 2, false, cur, b, oth, c.omega));
+    else RET(op_poisson(p, l, 2, cur, b, oth, c.omega));
+    std::swap(cur, oth);
+  }
+  if (isF) RET(op_stokes(p, l, 1, false, cur, b, r, 0.0));
+  else RET(op_poisson(p, l, 1, cur, b, r, 0.0));
+  RET(op_restrict(p, l, isF, r));
+  Level& cl = p->lev[l + 1];
+  RET(vcycle(p, l + 1, isF, isF ? cl.bF : cl.bP, isF ? cl.xF : cl.xP));
+  RET(op_prolong_add(p, l, isF, cur));
+  for (int s = 0; s < c.nu2; ++s) {
+    if (isF) RET(op_stokes(p, l, 2, false, cur, b, oth, c.omega));
+    else RET(op_poisson(p, l, 2, cur, b, oth, c.omega));
+    std::swap(cur, oth);
+  }
+  if (cur != x) return set_err(MPBP_E_STATE, "internal: V-cycle ping-pong parity");
+  return 0;
+}
+
+static int project_mean(mpbp_plan* p, double* x) {
+  Level& v = p->lev[0];
+  const size_t len = v.fs();
+  const int blocks = (int)std::min<size_t>((len + kRedThreads - 1) / kRedThreads, (size_t)p->red_blocks);
+  double* s = p->scal + kScal - 1;
+  k_sum<<<blocks, kRedThreads, 0, p->st>>>(x, len, p->partial, p->counter, s);
+  LAUNCH_CHECK(p);
+  RET(allreduce_scal(p, s, 1));
+  k_shift_dev<<<ew_blocks(len), 256, 0, p->st>>>(s, 1.0 / ((double)v.n * (double)v.n), x, len);
+  LAUNCH_CHECK(p);
+  return 0;
+}
+
+// x = F~^-1 b  /  x = (GtG)~^-1 b  (fixed linear operators; zero initial guess)
+static int sub_solve(mpbp_plan* p, bool isF, const double* b, double* x) {
+  const mpbp_config& c = p->cfg;
+  Level& v = p->lev[0];
+  const size_t len = (isF ? 4 : 1) * v.fs();
+  const int kind = isF ? c.F_kind : c.P_kind;
+  if (c.operators_only) return set_err(MPBP_E_STATE, "plan was created with operators_only");
+  if (kind == MPBP_SUB_JACOBI) {
+    const int sweeps = isF ? c.F_sweeps : c.P_sweeps;
+    if (sweeps < 1) return set_err(MPBP_E_ARG, "sweeps must be >= 1");
+    if (isF) RET(op_jacobi0_F(p, 0, b, x, c.omega));
+    else RET(op_poisson(p, 0, 3, nullptr, b, x, c.omega));
+    RET(jacobi_sweeps(p, 0, isF, b, x, isF ? v.tF : v.tP, sweeps - 1, c.omega));
+  } else {
+    const int cycles = isF ? c.F_cycles : c.P_cycles;
+    if (cycles < 1) return set_err(MPBP_E_ARG, "cycles must be >= 1");
+    double* rin = isF ? p->rinF : p->rinP;
+    double* z = isF ? p->zF : p->zP;
+    double* dv = isF ? p->dvF : p->dvP;
+    if (!c.cheb) {
+      RET(vcycle(p, 0, isF, b, x));
+      for (int k = 1; k < cycles; ++k) {
+        if (isF) RET(op_stokes(p, 0, 1, false, x, b, rin, 0.0));
+        else RET(op_poisson(p, 0, 1, x, b, rin, 0.0));
+        RET(vcycle(p, 0, isF, rin, z));
+        RET(v_axpby(p, 1.0, x, 1.0, z, x, len));
+      }
+    } else {
+      // Chebyshev semi-iteration on (V-cycle) o A, spectrum in [lmin, lmax]
+      const double th = 0.5 * (c.lmax + c.lmin), de = 0.5 * (c.lmax - c.lmin);
+      const double sig = th / de;
+      double rho_k = 1.0 / sig;
+      RET(vcycle(p, 0, isF, b, z));
+      RET(v_axpby(p, 1.0 / th, z, 0.0, z, dv, len));
+      RET(v_copy(p, dv, x, len));
+      for (int k = 1; k < cycles; ++k) {
+        if (isF) RET(op_stokes(p, 0, 1, false, x, b, rin, 0.0));
+        else RET(op_poisson(p, 0, 1, x, b, rin, 0.0));
+        RET(vcycle(p, 0, isF, rin, z));
+        const double rho_n = 1.0 / (2.0 * sig - rho_k);
+        k_cheb_update<<<ew_blocks(len), 256, 0, p->st>>>(rho_n * rho_k, 2.0 * rho_n / de, z, dv, x, len);
+        LAUNCH_CHECK(p);
+        rho_k = rho_n;
+      }
+    }
+  }
+  if (!isF && c.project) RET(project_mean(p, x));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the preconditioner apply: approx_schur_op, solve.py:257-277
+// ---------------------------------------------------------------------------------------------
+static int precond_apply(mpbp_plan* p, const double* v, double* z) {
+  const size_t fs = p->lev[0].fs();
+  RET(sub_solve(p, true, v, p->w));                       // :258  Finv_v = F_inv @ v[:4N]
+  RET(op_div(p, 0, p->w, v + 4 * fs, p->rhs, 1.0));       // :259  rhs_interim = D Finv_v + v[4N:]
+  RET(sub_solve(p, false, p->rhs, p->xa));                // :265  x_a = (GtG)~^-1 rhs_interim
+  RET(op_grad(p, 0, p->xa, p->g));                        // :267  x_b = Gt_F_G x_a = -D F G x_a   (:246-249)
+  RET(op_stokes(p, 0, 0, false, p->g, nullptr, p->t2, 0.0));
+  RET(op_div(p, 0, p->t2, nullptr, p->xb, -1.0));
+  RET(sub_solve(p, false, p->xb, z + 4 * fs));            // :271  x_p = (GtG)~^-1 x_b
+  RET(op_grad(p, 0, z + 4 * fs, p->g));                   // :273  G_xp = G x_p
+  RET(sub_solve(p, true, p->g, p->t2));                   // :274  Finv_G_xp = F_inv @ G_xp
+  RET(v_axpby(p, 1.0, p->w, -1.0, p->t2, z, 4 * fs));     // :275  u = Finv_v - Finv_G_xp ; :276 concat
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan creation
+// ---------------------------------------------------------------------------------------------
+extern "C" int mpbp_config_default(mpbp_config* c) {
+  if (!c) return set_err(MPBP_E_ARG, "null config");
+  memset(c, 0, sizeof(*c));
+  c->n = 16;  // solve.py:291
+  c->xi = 1.0;
+  c->eta_n = 100.0;
+  c->eta_s = 1.0;  // solve.py:295-297
+  c->c = 1.0;
+  c->d_u = -1.0;  // solve.py:292-293
+  c->d_p = 1.0;
+  c->d_div = -1.0;  // preconditioner.py:299
+  c->rank = 0;
+  c->nranks = 1;
+  c->F_kind = c->P_kind = MPBP_SUB_MG;
+  c->F_sweeps = c->P_sweeps = 20;
+  c->F_cycles = 4;
+  c->P_cycles = 2;
+  c->omega = 0.8;
+  c->nu1 = c->nu2 = 2;
+  c->n_coarse = 4;
+  c->cheb = 1;
+  c->lmin = 0.75;
+  c->lmax = 1.2;
+  c->project = 1;
+  return 0;
+}
+
+static int check_cfg(const mpbp_config* c) {
+  if (!c) return set_err(MPBP_E_ARG, "null config");
+  if (c->n < 2) return set_err(MPBP_E_ARG, "n must be >= 2 (got %d)", c->n);
+  if (c->nranks < 1 || c->rank < 0 || c->rank >= c->nranks) return set_err(MPBP_E_ARG, "bad rank/nranks");
+  if (c->nranks > 1 && !c->nccl_unique_id) return set_err(MPBP_E_ARG, "nranks>1 needs nccl_unique_id");
+  if (c->n_coarse < 2 || c->n_coarse > 8) return set_err(MPBP_E_ARG, "n_coarse must be in [2,8]");
+  if (!(c->omega > 0.0)) return set_err(MPBP_E_ARG, "omega must be > 0");
+  if (c->cheb && !(c->lmax > c->lmin && c->lmin > 0.0)) return set_err(MPBP_E_ARG, "need 0 < lmin < lmax");
+  return 0;
+}
+
+extern "C" int mpbp_plan_workspace_bytes(const mpbp_config* cfg, size_t* bytes) {
+  RET(check_cfg(cfg));
+  if (!bytes) return set_err(MPBP_E_ARG, "null bytes");
+  mpbp_plan tmp;
+  tmp.cfg = *cfg;
+  RET(build_levels_shape(*cfg, tmp.lev, tmp.first_repl));
+  Bump B;
+  B.dry = true;
+  carve(&tmp, B);
+  *bytes = B.off + 256;
+  return 0;
+}
+
+// dense inverse by Gauss-Jordan with partial pivoting (row-major, in place); returns false if singular
+static bool invert_dense(std::vector<double>& A, int m) {
+  std::vector<double> I((size_t)m * m, 0.0);
+  for (int i = 0; i < m; ++i) I[(size_t)i * m + i] = 1.0;
+  for (int col = 0; col < m; ++col) {
+    int piv = col;
+    double best = std::fabs(A[(size_t)col * m + col]);
+    for (int r = col + 1; r < m; ++r) {
+      const double v = std::fabs(A[(size_t)r * m + col]);
+      if (v > best) best = v, piv = r;
+    }
+    if (best == 0.0) return false;
+    if (piv != col)
+      for (int k = 0; k < m; ++k) {
+        std::swap(A[(size_t)piv * m + k], A[(size_t)col * m + k]);
+        std::swap(I[(size_t)piv * m + k], I[(size_t)col * m + k]);
+      }
+    const double d = 1.0 / A[(size_t)col * m + col];
+    for (int k = 0; k < m; ++k) {
+      A[(size_t)col * m + k] *= d;
+      I[(size_t)col * m + k] *= d;
+    }
+    for (int r = 0; r < m; ++r) {
+      if (r == col) continue;
+      const double f = A[(size_t)r * m + col];
+      if (f == 0.0) continue;
+      for (int k = 0; k < m; ++k) {
+        A[(size_t)r * m + k] -= f * A[(size_t)col * m + k];
+        I[(size_t)r * m + k] -= f * I[(size_t)col * m + k];
+      }
+    }
+  }
+  A.swap(I);
+  return true;
+}
+
+static int build_coarse_inverses(mpbp_plan* p) {
+  const int l = (int)p->lev.size() - 1;
+  Level& v = p->lev[l];
+  // scratch: two vectors of the coarsest level.  With a single level the per-level x/b buffers do
+  // not exist, so borrow level-0 scratch.
+  double* xin = (l > 0) ? v.bF : p->w;
+  double* yout = (l > 0) ? v.xF : p->g;
+  for (int pass = 0; pass < 2; ++pass) {
+    const bool isF = pass == 0;
+    const int m = isF ? p->mF : p->mP;
+    std::vector<double> M((size_t)m * m), col(m);
+    const double one = 1.0;
+    for (int j = 0; j < m; ++j) {
+      CU(cudaMemsetAsync(xin, 0, m * sizeof(double), p->st));
+      CU(cudaMemcpyAsync(xin + j, &one, sizeof(double), cudaMemcpyHostToDevice, p->st));
+      if (isF) RET(op_stokes(p, l, 0, false, xin, nullptr, yout, 0.0));
+      else RET(op_poisson(p, l, 0, xin, nullptr, yout, 0.0));
+      CU(cudaMemcpyAsync(col.data(), yout, m * sizeof(double), cudaMemcpyDeviceToHost, p->st));
+      CU(cudaStreamSynchronize(p->st));
+      for (int i = 0; i < m; ++i) M[(size_t)i * m + j] = col[i];
+    }
+    if (!isF) {
+      // GtG is singular (constants): pseudo-inverse = (M + e e^T)^-1 - e e^T, e = 1/sqrt(m)
+      const double ee = 1.0 / m;
+      for (size_t i = 0; i < M.size(); ++i) M[i] += ee;
+      if (!invert_dense(M, m)) return set_err(MPBP_E_STATE, "coarse GtG + ee^T is singular");
+      for (size_t i = 0; i < M.size(); ++i) M[i] -= ee;
+    } else if (!invert_dense(M, m)) {
+      return set_err(MPBP_E_STATE, "coarse F is singular");
+    }
+    // column-major upload: Mt[k*m+i] = M[i][k]
+    std::vector<double> Mt((size_t)m * m);
+    for (int i = 0; i < m; ++i)
+      for (int k = 0; k < m; ++k) Mt[(size_t)k * m + i] = M[(size_t)i * m + k];
+    CU(cudaMemcpyAsync(isF ? p->FinvT : p->PinvT, Mt.data(), Mt.size() * sizeof(double), cudaMemcpyHostToDevice, p->st));
+    CU(cudaStreamSynchronize(p->st));
+  }
+  return 0;
+}
+
+extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
+  if (!out) return set_err(MPBP_E_ARG, "null plan pointer");
+  *out = nullptr;
+  RET(check_cfg(cfg));
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (ndev < 1) return set_err(MPBP_E_STATE, "no CUDA device: libmpbp has no CPU fallback");
+  mpbp_plan* p = new mpbp_plan();
+  p->cfg = *cfg;
+  p->cfg.theta_host = nullptr;
+  p->cfg.nccl_unique_id = nullptr;
+  p->nranks = cfg->nranks;
+  p->rank = cfg->rank;
+  int rc = build_levels_shape(*cfg, p->lev, p->first_repl);
+  if (rc) { delete p; return rc; }
+  Bump B;
+  B.dry = true;
+  carve(p, B);
+  const size_t need = B.off + 256;
+  char* base = nullptr;
+  if (cfg->workspace) {
+    if (cfg->workspace_bytes < need) {
+      delete p;
+      return set_err(MPBP_E_NOMEM, "workspace too small: %zu < %zu", cfg->workspace_bytes, need);
+    }
+    base = (char*)cfg->workspace;
+  } else {
+    cudaError_t e = cudaMalloc(&p->owned, need);
+    if (e != cudaSuccess) {
+      delete p;
+      return set_err((int)e, "cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+    }
+    base = (char*)p->owned;
+  }
+  B = Bump();
+  B.base = (char*)(((uintptr_t)base + 255) & ~uintptr_t(255));
+  B.dry = false;
+  carve(p, B);
+  {
+    cudaError_t e = cudaMallocHost(&p->hscal, kScal * sizeof(double));
+    if (e != cudaSuccess) { mpbp_plan_destroy(p); return set_err((int)e, "cudaMallocHost failed"); }
+  }
+  p->st = nullptr;
+  auto fail = [&](int code) { mpbp_plan_destroy(p); return code; };
+  if (cudaMemsetAsync(p->counter, 0, 64 * sizeof(unsigned int), nullptr) != cudaSuccess)
+    return fail(set_err(999, "memset failed"));
+
+  if (p->nranks > 1) {
+    ncclUniqueId id;
+    memcpy(&id, cfg->nccl_unique_id, sizeof(id));
+    ncclResult_t e = ncclCommInitRank(&p->comm, p->nranks, id, p->rank);
+    if (e != ncclSuccess) return fail(set_err(1000 + (int)e, "ncclCommInitRank: %s", ncclGetErrorString(e)));
+  }
+
+  // ---- coefficient fields on the host: theta_n per level (4-cell averages), mass-term tables ----
+  const int n0 = cfg->n;
+  const double PI = 3.141592653589793;
+  {
+    std::vector<double> sxf(n0), sxc(n0), syf(n0), syc(n0);
+    const double h = 1.0 / n0;
+    for (int i = 0; i < n0; ++i) {
+      sxf[i] = std::sin(2 * PI * (i * h));            // x = c h            (preconditioner.py:325)
+      sxc[i] = std::sin(2 * PI * ((i + 0.5) * h));    // x = (c+1/2) h      (preconditioner.py:326)
+      syf[i] = std::sin(2 * PI * (-i * h));           // y = -r h
+      syc[i] = std::sin(2 * PI * (-(i + 0.5) * h));   // y = -(r+1/2) h
+    }
+    std::vector<double> th((size_t)n0 * n0);
+    if (cfg->theta_host) {
+      memcpy(th.data(), cfg->theta_host, th.size() * sizeof(double));
+    } else {
+      for (int r = 0; r < n0; ++r)
+        for (int c = 0; c < n0; ++c) th[(size_t)r * n0 + c] = 0.25 * sxc[c] * syc[r] + 0.5;  // preconditioner.py:10
+    }
+    cudaMemcpy(p->sxf, sxf.data(), n0 * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(p->sxc, sxc.data(), n0 * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(p->syf, syf.data(), n0 * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(p->syc, syc.data(), n0 * sizeof(double), cudaMemcpyHostToDevice);
+    for (size_t l = 0; l < p->lev.size(); ++l) {
+      Level& v = p->lev[l];
+      const int n = v.n;
+      if (l > 0) {
+        std::vector<double> tc((size_t)n * n);
+        const int nf = 2 * n;
+        for (int R = 0; R < n; ++R)
+          for (int C = 0; C < n; ++C) {
+            const double* a = &th[(size_t)(2 * R) * nf + 2 * C];
+            tc[(size_t)R * n + C] = 0.25 * (a[0] + a[nf] + a[1] + a[nf + 1]);
+          }
+        th.swap(tc);
+      }
+      // upload rows row0-1 .. row0+rows (periodic)
+      std::vector<double> pad((size_t)(v.rows + 2) * n);
+      for (int r = -1; r <= v.rows; ++r) {
+        const int gr = ((v.row0 + r) % n + n) % n;
+        memcpy(&pad[(size_t)(r + 1) * n], &th[(size_t)gr * n], n * sizeof(double));
+      }
+      if (cudaMemcpy(v.th, pad.data(), pad.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(set_err(999, "theta upload failed: %s", cudaGetErrorString(cudaGetLastError())));
+      const double h = 1.0 / n;
+      Phys& ph = v.ph;
+      ph.xi = cfg->xi;
+      ph.c = cfg->c;
+      ph.d_u = cfg->d_u;
+      ph.kap_n = cfg->d_u * cfg->eta_n / (h * h);
+      ph.kap_s = cfg->d_u * cfg->eta_s / (h * h);
+      ph.dp_h = cfg->d_p / h;
+      ph.ddiv_h = cfg->d_div / h;
+      ph.inv_h = 1.0 / h;
+      ph.dp_h2 = cfg->d_p / (h * h);
+      ph.mass_mode = (l == 0 && !cfg->theta_host) ? 1 : 0;
+      ph.sxf = p->sxf;
+      ph.sxc = p->sxc;
+      ph.syf = p->syf;
+      ph.syc = p->syc;
+      v.geo.n = n;
+      v.geo.rows = v.rows;
+      v.geo.row0 = v.row0;
+      int rs = 32;
+      const int gx = (n + kWarpCols * kBlockWarps - 1) / (kWarpCols * kBlockWarps);
+      while (rs > 4 && gx * ((v.rows + rs - 1) / rs) < 592) rs /= 2;
+      v.geo.rs = std::max(1, std::min(rs, v.rows));
+    }
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  p->red_blocks = std::min(kMaxRedBlocks, sms * 4);
+  if (!cfg->operators_only) {
+    rc = build_coarse_inverses(p);
+    if (rc) return fail(rc);
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) return fail(set_err(999, "plan setup failed: %s", cudaGetErrorString(cudaGetLastError())));
+  p->launches = 0;
+  *out = p;
+  return 0;
+}
+
+extern "C" int mpbp_plan_destroy(mpbp_plan* p) {
+  if (!p) return 0;
+  cudaDeviceSynchronize();
+  if (p->comm) ncclCommDestroy(p->comm);
+  if (p->owned) cudaFree(p->owned);
+  if (p->kry_owned) cudaFree(p->kry_owned);
+  for (int i = 0; i < 2; ++i)
+    if (p->hostbuf_dev[i]) cudaFree(p->hostbuf_dev[i]);
+  if (p->hscal) cudaFreeHost(p->hscal);
+  delete p;
+  return 0;
+}
+
+extern "C" const char* mpbp_last_error_string(void) { return g_err; }
+
+extern "C" int mpbp_nccl_unique_id(void* out128) {
+  if (!out128) return set_err(MPBP_E_ARG, "null output");
+  ncclUniqueId id;
+  NC(ncclGetUniqueId(&id));
+  static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(out128, &id, sizeof(id));
+  return 0;
+}
+
+extern "C" int mpbp_plan_rows_local(const mpbp_plan* p) { return p ? p->lev[0].rows : MPBP_E_ARG; }
+extern "C" int mpbp_plan_num_levels(const mpbp_plan* p) { return p ? (int)p->lev.size() : MPBP_E_ARG; }
+extern "C" long long mpbp_plan_launches(const mpbp_plan* p) { return p ? p->launches : -1; }
+
+// ---------------------------------------------------------------------------------------------
+// exported operator applies
+// ---------------------------------------------------------------------------------------------
+#define ENTER(p, stream)                               \
+  if (!(p)) return set_err(MPBP_E_ARG, "null plan");   \
+  (p)->st = (cudaStream_t)(stream);
+
+extern "C" int mpbp_apply_A(mpbp_plan* p, const double* x, double* y, void* stream) {
+  ENTER(p, stream);
+  if (!x || !y || x == y) return set_err(MPBP_E_ARG, "apply_A: bad pointers");
+  return op_stokes(p, 0, 0, true, x, nullptr, y, 0.0);
+}
+extern "C" int mpbp_apply_F(mpbp_plan* p, const double* x, double* y, void* stream) {
+  ENTER(p, stream);
+  if (!x || !y || x == y) return set_err(MPBP_E_ARG, "apply_F: bad pointers");
+  return op_stokes(p, 0, 0, false, x, nullptr, y, 0.0);
+}
+extern "C" int mpbp_apply_G(mpbp_plan* p, const double* pr, double* y, void* stream) {
+  ENTER(p, stream);
+  if (!pr || !y) return set_err(MPBP_E_ARG, "apply_G: bad pointers");
+  return op_grad(p, 0, pr, y);
+}
+extern "C" int mpbp_apply_D(mpbp_plan* p, const double* w, const double* add, double* r, void* stream) {
+  ENTER(p, stream);
+  if (!w || !r) return set_err(MPBP_E_ARG, "apply_D: bad pointers");
+  return op_div(p, 0, w, add, r, 1.0);
+}
+extern "C" int mpbp_apply_GtG(mpbp_plan* p, const double* pr, double* y, void* stream) {
+  ENTER(p, stream);
+  if (!pr || !y || pr == y) return set_err(MPBP_E_ARG, "apply_GtG: bad pointers");
+  return op_poisson(p, 0, 0, pr, nullptr, y, 0.0);
+}
+extern "C" int mpbp_apply_GtFG(mpbp_plan* p, const double* pr, double* y, void* stream) {
+  ENTER(p, stream);
+  if (!pr || !y) return set_err(MPBP_E_ARG, "apply_GtFG: bad pointers");
+  RET(op_grad(p, 0, pr, p->g));
+  RET(op_stokes(p, 0, 0, false, p->g, nullptr, p->t2, 0.0));
+  return op_div(p, 0, p->t2, nullptr, y, -1.0);
+}
+extern "C" int mpbp_jacobi_F(mpbp_plan* p, const double* b, double* x, int sweeps, double omega, void* stream) {
+  ENTER(p, stream);
+  if (!b || !x || sweeps < 0) return set_err(MPBP_E_ARG, "jacobi_F: bad arguments");
+  return jacobi_sweeps(p, 0, true, b, x, p->lev[0].tF, sweeps, omega);
+}
+extern "C" int mpbp_jacobi_P(mpbp_plan* p, const double* b, double* x, int sweeps, double omega, void* stream) {
+  ENTER(p, stream);
+  if (!b || !x || sweeps < 0) return set_err(MPBP_E_ARG, "jacobi_P: bad arguments");
+  return jacobi_sweeps(p, 0, false, b, x, p->lev[0].tP, sweeps, omega);
+}
+extern "C" int mpbp_vcycle_F(mpbp_plan* p, const double* b, double* x, void* stream) {
+  ENTER(p, stream);
+  if (!b || !x || b == x) return set_err(MPBP_E_ARG, "vcycle_F: bad pointers");
+  return vcycle(p, 0, true, b, x);
+}
+extern "C" int mpbp_vcycle_P(mpbp_plan* p, const double* b, double* x, void* stream) {
+  ENTER(p, stream);
+  if (!b || !x || b == x) return set_err(MPBP_E_ARG, "vcycle_P: bad pointers");
+  return vcycle(p, 0, false, b, x);
+}
+extern "C" int mpbp_solve_F(mpbp_plan* p, const double* b, double* x, void* stream) {
+  ENTER(p, stream);
+  if (!b || !x || b == x) return set_err(MPBP_E_ARG, "solve_F: bad pointers");
+  return sub_solve(p, true, b, x);
+}
+extern "C" int mpbp_solve_P(mpbp_plan* p, const double* b, double* x, void* stream) {
+  ENTER(p, stream);
+  if (!b || !x || b == x) return set_err(MPBP_E_ARG, "solve_P: bad pointers");
+  return sub_solve(p, false, b, x);
+}
+extern "C" int mpbp_precond_apply(mpbp_plan* p, const double* v, double* z, void* stream) {
+  ENTER(p, stream);
+  if (!v || !z || v == z) return set_err(MPBP_E_ARG, "precond_apply: bad pointers");
+  return precond_apply(p, v, z);
+}
+
+static int ensure_hostbuf(mpbp_plan* p) {
+  const size_t bytes = 5 * p->lev[0].fs() * sizeof(double);
+  for (int i = 0; i < 2; ++i)
+    if (!p->hostbuf_dev[i]) CU(cudaMalloc(&p->hostbuf_dev[i], bytes));
+  return 0;
+}
+extern "C" int mpbp_precond_apply_host(mpbp_plan* p, const double* v_host, double* z_host, void* stream) {
+  ENTER(p, stream);
+  if (!v_host || !z_host) return set_err(MPBP_E_ARG, "precond_apply_host: bad pointers");
+  RET(ensure_hostbuf(p));
+  const size_t bytes = 5 * p->lev[0].fs() * sizeof(double);
+  CU(cudaMemcpyAsync(p->hostbuf_dev[0], v_host, bytes, cudaMemcpyHostToDevice, p->st));
+  RET(precond_apply(p, p->hostbuf_dev[0], p->hostbuf_dev[1]));
+  CU(cudaMemcpyAsync(z_host, p->hostbuf_dev[1], bytes, cudaMemcpyDeviceToHost, p->st));
+  CU(cudaStreamSynchronize(p->st));
+  return 0;
+}
+
+// algorithmic bytes (SURVEY 8d accounting: every input read once, every output written once, one
+// coefficient field per stencil kernel) of one preconditioner apply under the current configuration
+static double vcycle_bytes(const mpbp_plan* p, int l, bool isF) {
+  const mpbp_config& c = p->cfg;
+  const int L = (int)p->lev.size();
+  const double N = (double)p->lev[l].fs();
+  if (l == L - 1) return 0.0;  // dense coarse solve: negligible
+  double by = 0.0;
+  if (isF) {
+    by += 72 * N;                          // first sweep from x=0
+    by += (c.nu1 - 1 + c.nu2) * 104.0 * N; // Jacobi sweeps
+    by += 104 * N;                         // residual
+    by += 40 * N;                          // restrict (read 4N, write N)
+    by += 72 * N;                          // prolong + correct (read 4N + N, write 4N)
+  } else {
+    by += 24 * N;
+    by += (c.nu1 - 1 + c.nu2) * 32.0 * N;
+    by += 32 * N;
+    by += 10 * N;
+    by += 18 * N;
+  }
+  return by + vcycle_bytes(p, l + 1, isF);
+}
+static double solve_bytes(const mpbp_plan* p, bool isF) {
+  const mpbp_config& c = p->cfg;
+  const double N = (double)p->lev[0].fs();
+  const int kind = isF ? c.F_kind : c.P_kind;
+  double by = 0.0;
+  if (kind == MPBP_SUB_JACOBI) {
+    const int s = isF ? c.F_sweeps : c.P_sweeps;
+    by = isF ? (72 * N + (s - 1) * 104.0 * N) : (24 * N + (s - 1) * 32.0 * N);
+  } else {
+    const int k = isF ? c.F_cycles : c.P_cycles;
+    const double vec = isF ? 32 * N : 8 * N;  // one vector pass
+    by = k * vcycle_bytes(p, 0, isF);
+    by += (k - 1) * (isF ? 104 * N : 32 * N);                 // residual before every extra cycle
+    by += (k - 1) * (c.cheb ? 5 * vec : 3 * vec);             // x += z  / Chebyshev update
+    if (c.cheb) by += 4 * vec;                                // d = z/theta ; x = d
+  }
+  if (!isF && c.project) by += 3 * 8 * N;
+  return by;
+}
+extern "C" int mpbp_precond_bytes(const mpbp_plan* p, double* bytes) {
+  if (!p || !bytes) return set_err(MPBP_E_ARG, "null argument");
+  const double N = (double)p->lev[0].fs();
+  double by = 2 * solve_bytes(p, true) + 2 * solve_bytes(p, false);
+  by += 56 * N;             // K5  r = D w + v_p
+  by += 48 * N + 72 * N + 48 * N;  // K7 -> K2 -> K5 chain for GtFG
+  by += 48 * N;             // K7  G x_p
+  by += 96 * N;             // K8  w - y
+  *bytes = by;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// exported vector kernels
+// ---------------------------------------------------------------------------------------------
+extern "C" int mpbp_dot(mpbp_plan* p, const double* x, const double* y, size_t len, double* result, void* stream) {
+  ENTER(p, stream);
+  if (!x || !y || !result) return set_err(MPBP_E_ARG, "dot: bad pointers");
+  RET(v_dot(p, x, y, len, p->scal));
+  RET(fetch_scal(p, p->scal, 1, p->hscal));
+  *result = p->hscal[0];
+  return 0;
+}
+extern "C" int mpbp_nrm2(mpbp_plan* p, const double* x, size_t len, double* result, void* stream) {
+  ENTER(p, stream);
+  if (!x || !result) return set_err(MPBP_E_ARG, "nrm2: bad pointers");
+  RET(v_nrm2(p, x, len, p->scal));
+  RET(fetch_scal(p, p->scal, 1, p->hscal));
+  *result = p->hscal[0];
+  return 0;
+}
+extern "C" int mpbp_axpy(mpbp_plan* p, double alpha, const double* x, double* y, size_t len, void* stream) {
+  ENTER(p, stream);
+  if (!x || !y) return set_err(MPBP_E_ARG, "axpy: bad pointers");
+  return v_multi_axpy(p, x, 0, 1, &alpha, y, len);
+}
+extern "C" int mpbp_multi_dot(mpbp_plan* p, const double* V, size_t ld, int nvec, const double* w, size_t len,
+                              double* out, void* stream) {
+  ENTER(p, stream);
+  if (!V || !w || !out || nvec < 1 || nvec > kScal - 8) return set_err(MPBP_E_ARG, "multi_dot: bad arguments");
+  RET(v_multi_dot(p, V, ld, nvec, w, len, p->scal, false));
+  RET(fetch_scal(p, p->scal, nvec, p->hscal));
+  memcpy(out, p->hscal, nvec * sizeof(double));
+  return 0;
+}
+extern "C" int mpbp_multi_axpy(mpbp_plan* p, const double* V, size_t ld, int nvec, const double* alpha, double* w,
+                               size_t len, void* stream) {
+  ENTER(p, stream);
+  if (!V || !w || !alpha || nvec < 1) return set_err(MPBP_E_ARG, "multi_axpy: bad arguments");
+  return v_multi_axpy(p, V, ld, nvec, alpha, w, len);
+}
+extern "C" int mpbp_wnorms(mpbp_plan* p, const double* a, const double* b, size_t len, double w, double* out3,
+                           void* stream) {
+  ENTER(p, stream);
+  if (!a || !b || !out3) return set_err(MPBP_E_ARG, "wnorms: bad pointers");
+  const int blocks = (int)std::min<size_t>((len + kRedThreads - 1) / kRedThreads, (size_t)p->red_blocks);
+  k_diffnorms<<<blocks, kRedThreads, 0, p->st>>>(a, b, len, p->partial, p->counter, p->scal);
+  LAUNCH_CHECK(p);
+  if (p->nranks > 1) {
+    NC(ncclAllReduce(p->scal, p->scal, 2, ncclDouble, ncclSum, p->comm, p->st));
+    NC(ncclAllReduce(p->scal + 2, p->scal + 2, 1, ncclDouble, ncclMax, p->comm, p->st));
+  }
+  RET(fetch_scal(p, p->scal, 3, p->hscal));
+  out3[0] = w * p->hscal[0];        // weighted_L1, utils.py:11-14
+  out3[1] = sqrt(w * p->hscal[1]);  // weighted_L2, utils.py:7-9
+  out3[2] = p->hscal[2];            // max_norm,    utils.py:16-17
+  return 0;
+}
+extern "C" int mpbp_fill_manufactured(mpbp_plan* p, double* u_vec, double* b_vec, double b_p_sign, void* stream) {
+  ENTER(p, stream);
+  const Level& v = p->lev[0];
+  const mpbp_config& c = p->cfg;
+  const dim3 block(128), grid((v.n + 127) / 128, v.rows);
+  k_fill_manufactured<<<grid, block, 0, p->st>>>(u_vec, b_vec, v.n, v.rows, v.row0, c.c, c.d_u, c.xi, c.eta_n, c.eta_s,
+                                                  b_p_sign);
+  LAUNCH_CHECK(p);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Krylov
+// ---------------------------------------------------------------------------------------------
+extern "C" int mpbp_gmres_opts_default(mpbp_gmres_opts* o) {
+  if (!o) return set_err(MPBP_E_ARG, "null opts");
+  memset(o, 0, sizeof(*o));
+  o->rtol = 1e-8;     // solve.py:285
+  o->restart = 20;    // scipy default
+  o->maxiter = 150;   // solve.py:285
+  o->side = MPBP_SIDE_RIGHT;
+  o->use_precond = 1;
+  return 0;
+}
+static size_t kry_vectors(const mpbp_gmres_opts* o) {
+  // V: restart+1, w, tmp ; right: + Z: restart
+  return (size_t)(o->restart + 1) + 2 + (o->side == MPBP_SIDE_RIGHT ? (size_t)o->restart : 0);
+}
+extern "C" int mpbp_gmres_workspace_bytes(const mpbp_plan* p, const mpbp_gmres_opts* o, size_t* bytes) {
+  if (!p || !o || !bytes) return set_err(MPBP_E_ARG, "null argument");
+  if (o->restart < 1) return set_err(MPBP_E_ARG, "restart must be >= 1");
+  *bytes = kry_vectors(o) * 5 * p->lev[0].fs() * sizeof(double) + 256;
+  return 0;
+}
+
+// LAPACK dlartg: [c s; -s c] [f; g] = [r; 0]
+static void lartg(double f, double g, double& c, double& s, double& r) {
+  if (g == 0.0) { c = 1.0; s = 0.0; r = f; return; }
+  if (f == 0.0) { c = 0.0; s = (g < 0 ? -1.0 : 1.0); r = std::fabs(g); return; }
+  const double d = std::sqrt(f * f + g * g);
+  c = std::fabs(f) / d;
+  r = (f < 0 ? -d : d);
+  s = g / r;
+}
+
+static int psolve(mpbp_plan* p, bool use_pc, const double* in, double* out, size_t len) {
+  if (use_pc) return precond_apply(p, in, out);
+  return v_copy(p, in, out, len);
+}
+
+// scipy.sparse.linalg.gmres (scipy/sparse/linalg/_isolve/iterative.py) restated: left
+// preconditioning, modified Gram-Schmidt, Givens rotations, restart, presid/ptol tolerance control.
+static int gmres_left(mpbp_plan* p, const double* b, double* x, const mpbp_gmres_opts* o, double* ws, double* hist,
+                      int hist_cap, int* n_iters, int* info) {
+  const size_t len = 5 * p->lev[0].fs();
+  const int m = o->restart;
+  double* V = ws;                       // (m+1) x len
+  double* w = V + (size_t)(m + 1) * len;
+  double* tmp = w + len;
+  double* hs = p->hscal;
+  double* ds = p->scal;
+  const double eps = std::numeric_limits<double>::epsilon();
+  const bool pc = o->use_precond != 0;
+  const bool forced = o->force_iters > 0;
+  int inner_iter = 0;
+  *n_iters = 0;
+  *info = 0;
+
+  RET(v_nrm2(p, b, len, ds));
+  RET(fetch_scal(p, ds, 1, hs));
+  const double bnrm2 = hs[0];
+  const double atol = std::max(0.0, o->rtol * bnrm2);
+  if (bnrm2 == 0.0) { RET(v_copy(p, b, x, len)); return 0; }
+  if (!o->x0_nonzero) CU(cudaMemsetAsync(x, 0, len * sizeof(double), p->st));
+  RET(psolve(p, pc, b, tmp, len));
+  RET(v_nrm2(p, tmp, len, ds));
+  RET(fetch_scal(p, ds, 1, hs));
+  const double Mb_nrm2 = hs[0];
+  double ptol_max_factor = 1.0;
+  double ptol = Mb_nrm2 * std::min(ptol_max_factor, atol / bnrm2);
+  double presid = 0.0, rnorm = 0.0;
+  std::vector<double> H((size_t)m * (m + 1), 0.0), giv((size_t)m * 2, 0.0), S(m + 1), yv(m);
+  double* r = tmp;  // residual lives in tmp between outer iterations
+
+  for (int iteration = 0; iteration < o->maxiter; ++iteration) {
+    if (iteration == 0) {
+      if (o->x0_nonzero) {
+        RET(op_stokes(p, 0, 0, true, x, nullptr, w, 0.0));
+        RET(v_axpby(p, 1.0, b, -1.0, w, r, len));
+      } else {
+        RET(v_copy(p, b, r, len));
+      }
+      RET(v_nrm2(p, r, len, ds));
+      RET(fetch_scal(p, ds, 1, hs));
+      if (hs[0] < atol && !forced) return 0;
+    }
+    RET(psolve(p, pc, r, V, len));
+    RET(v_nrm2(p, V, len, ds));
+    k_scale_dev<<<ew_blocks(len), 256, 0, p->st>>>(ds, 1, V, V, len);
+    LAUNCH_CHECK(p);
+    RET(fetch_scal(p, ds, 1, hs));
+    std::fill(S.begin(), S.end(), 0.0);
+    S[0] = hs[0];
+    bool breakdown = false;
+    int col = 0;
+    for (col = 0; col < m; ++col) {
+      double* vc = V + (size_t)col * len;
+      double* vn = V + (size_t)(col + 1) * len;
+      RET(op_stokes(p, 0, 0, true, vc, nullptr, tmp, 0.0));  // av = A v[col]
+      RET(psolve(p, pc, tmp, w, len));                       // w = M av
+      // modified Gram-Schmidt with device-resident coefficients: ds[0]=h0, ds[1+k]=h[col][k], ds[col+2]=h1
+      RET(v_nrm2(p, w, len, ds));
+      for (int k = 0; k <= col; ++k) {
+        RET(v_dot(p, V + (size_t)k * len, w, len, ds + 1 + k));
+        k_axpy_dev<<<ew_blocks(len), 256, 0, p->st>>>(ds + 1 + k, -1.0, V + (size_t)k * len, w, len);
+        LAUNCH_CHECK(p);
+      }
+      RET(v_nrm2(p, w, len, ds + col + 2));
+      k_scale_dev<<<ew_blocks(len), 256, 0, p->st>>>(ds + col + 2, 1, w, vn, len);
+      LAUNCH_CHECK(p);
+      RET(fetch_scal(p, ds, col + 3, hs));
+      const double h0 = hs[0], h1 = hs[col + 2];
+      double* h = &H[(size_t)col * (m + 1)];
+      for (int k = 0; k <= col; ++k) h[k] = hs[1 + k];
+      h[col + 1] = h1;
+      if (h1 <= eps * h0) {
+        h[col + 1] = 0.0;
+        breakdown = true;
+      }
+      for (int k = 0; k < col; ++k) {
+        const double c = giv[2 * k], s = giv[2 * k + 1];
+        const double n0 = h[k], n1 = h[k + 1];
+        h[k] = c * n0 + s * n1;
+        h[k + 1] = -s * n0 + c * n1;
+      }
+      double c, s, mag;
+      lartg(h[col], h[col + 1], c, s, mag);
+      giv[2 * col] = c;
+      giv[2 * col + 1] = s;
+      h[col] = mag;
+      h[col + 1] = 0.0;
+      const double t = -s * S[col];
+      S[col] = c * S[col];
+      S[col + 1] = t;
+      presid = std::fabs(t);
+      inner_iter++;
+      if (hist && inner_iter <= hist_cap) hist[inner_iter - 1] = presid / bnrm2;
+      if (forced) {
+        if (inner_iter >= o->force_iters) break;
+      } else if (presid <= ptol || breakdown) {
+        break;
+      }
+    }
+    if (col == m) col = m - 1;
+    if (H[(size_t)col * (m + 1) + col] == 0.0) S[col] = 0.0;
+    for (int k = 0; k <= col; ++k) yv[k] = S[k];
+    for (int k = col; k > 0; --k) {
+      if (yv[k] != 0.0) {
+        yv[k] /= H[(size_t)k * (m + 1) + k];
+        const double t = yv[k];
+        for (int i = 0; i < k; ++i) yv[i] -= t * H[(size_t)k * (m + 1) + i];
+      }
+    }
+    if (yv[0] != 0.0) yv[0] /= H[0];
+    RET(v_multi_axpy(p, V, len, col + 1, yv.data(), x, len));
+    RET(op_stokes(p, 0, 0, true, x, nullptr, w, 0.0));
+    RET(v_axpby(p, 1.0, b, -1.0, w, r, len));
+    RET(v_nrm2(p, r, len, ds));
+    RET(fetch_scal(p, ds, 1, hs));
+    rnorm = hs[0];
+    if (forced) {
+      if (inner_iter >= o->force_iters) break;
+      continue;
+    }
+    if (rnorm <= atol) break;
+    else if (breakdown) break;
+    else if (presid <= ptol) ptol_max_factor = std::max(eps, 0.25 * ptol_max_factor);
+    else ptol_max_factor = std::min(1.0, 1.5 * ptol_max_factor);
+    ptol = presid * std::min(ptol_max_factor, atol / rnorm);
+  }
+  *n_iters = inner_iter;
+  *info = (rnorm <= atol) ? 0 : o->maxiter;
+  return 0;
+}
+
+// Right-preconditioned flexible GMRES with the call shape of pyamg.krylov.fgmres as used at
+// solve.py:285 (tol on ||r||/||b||, maxiter = total inner iterations, one cycle unless restart < maxiter).
+static int gmres_right(mpbp_plan* p, const double* b, double* x, const mpbp_gmres_opts* o, double* ws, double* hist,
+                       int hist_cap, int* n_iters, int* info) {
+  const size_t len = 5 * p->lev[0].fs();
+  const int m = o->restart;
+  double* V = ws;                              // (m+1) x len
+  double* Z = V + (size_t)(m + 1) * len;       // m x len
+  double* w = Z + (size_t)m * len;
+  double* tmp = w + len;
+  double* hs = p->hscal;
+  double* ds = p->scal;
+  const bool pc = o->use_precond != 0;
+  const bool forced = o->force_iters > 0;
+  const int maxit = forced ? o->force_iters : o->maxiter;
+  *n_iters = 0;
+  *info = maxit;
+  RET(v_nrm2(p, b, len, ds));
+  RET(fetch_scal(p, ds, 1, hs));
+  double bn = hs[0];
+  if (bn == 0.0) bn = 1.0;
+  if (!o->x0_nonzero) CU(cudaMemsetAsync(x, 0, len * sizeof(double), p->st));
+  std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), gv(m + 1), yv(m);
+  auto Hm = [&](int i, int j) -> double& { return H[(size_t)i * m + j]; };
+  int it = 0;
+  bool first = true;
+  while (it < maxit) {
+    if (first && !o->x0_nonzero) {
+      RET(v_copy(p, b, tmp, len));
+    } else {
+      RET(op_stokes(p, 0, 0, true, x, nullptr, w, 0.0));
+      RET(v_axpby(p, 1.0, b, -1.0, w, tmp, len));
+    }
+    first = false;
+    RET(v_nrm2(p, tmp, len, ds));
+    k_scale_dev<<<ew_blocks(len), 256, 0, p->st>>>(ds, 1, tmp, V, len);
+    LAUNCH_CHECK(p);
+    RET(fetch_scal(p, ds, 1, hs));
+    const double beta = hs[0];
+    if (beta < o->rtol * bn && !forced) { *info = 0; break; }
+    std::fill(gv.begin(), gv.end(), 0.0);
+    gv[0] = beta;
+    int jdone = 0;
+    double res = beta;
+    for (int j = 0; j < m; ++j) {
+      double* vj = V + (size_t)j * len;
+      double* zj = Z + (size_t)j * len;
+      RET(psolve(p, pc, vj, zj, len));                       // Z_j = M v_j
+      RET(op_stokes(p, 0, 0, true, zj, nullptr, w, 0.0));    // w = A Z_j
+      for (int i = 0; i <= j; ++i) {
+        RET(v_dot(p, V + (size_t)i * len, w, len, ds + i));
+        k_axpy_dev<<<ew_blocks(len), 256, 0, p->st>>>(ds + i, -1.0, V + (size_t)i * len, w, len);
+        LAUNCH_CHECK(p);
+      }
+      RET(v_nrm2(p, w, len, ds + j + 1));
+      k_scale_dev<<<ew_blocks(len), 256, 0, p->st>>>(ds + j + 1, 1, w, V + (size_t)(j + 1) * len, len);
+      LAUNCH_CHECK(p);
+      RET(fetch_scal(p, ds, j + 2, hs));
+      for (int i = 0; i <= j + 1; ++i) Hm(i, j) = hs[i];
+      for (int i = 0; i < j; ++i) {
+        const double t = cs[i] * Hm(i, j) + sn[i] * Hm(i + 1, j);
+        Hm(i + 1, j) = -sn[i] * Hm(i, j) + cs[i] * Hm(i + 1, j);
+        Hm(i, j) = t;
+      }
+      const double den = std::hypot(Hm(j, j), Hm(j + 1, j));
+      cs[j] = Hm(j, j) / den;
+      sn[j] = Hm(j + 1, j) / den;
+      Hm(j, j) = den;
+      Hm(j + 1, j) = 0.0;
+      gv[j + 1] = -sn[j] * gv[j];
+      gv[j] = cs[j] * gv[j];
+      it++;
+      jdone = j + 1;
+      res = std::fabs(gv[j + 1]);
+      if (hist && it <= hist_cap) hist[it - 1] = res / bn;
+      if ((!forced && res < o->rtol * bn) || it >= maxit) break;
+    }
+    // back substitution on the jdone x jdone triangle
+    for (int i = jdone - 1; i >= 0; --i) {
+      double s = gv[i];
+      for (int k = i + 1; k < jdone; ++k) s -= Hm(i, k) * yv[k];
+      yv[i] = s / Hm(i, i);
+    }
+    RET(v_multi_axpy(p, Z, len, jdone, yv.data(), x, len));
+    if (!forced && res < o->rtol * bn) { *info = 0; break; }
+  }
+  *n_iters = it;
+  return 0;
+}
+
+static int gmres_dispatch(mpbp_plan* p, const double* b, double* x, const mpbp_gmres_opts* o, double* hist,
+                          int hist_cap, int* n_iters, int* info) {
+  if (!o || o->restart < 1 || o->maxiter < 1) return set_err(MPBP_E_ARG, "gmres: bad options");
+  size_t need = 0;
+  RET(mpbp_gmres_workspace_bytes(p, o, &need));
+  double* ws = nullptr;
+  if (o->workspace) {
+    if (o->workspace_bytes < need) return set_err(MPBP_E_NOMEM, "gmres workspace too small: %zu < %zu", o->workspace_bytes, need);
+    ws = (double*)(((uintptr_t)o->workspace + 255) & ~uintptr_t(255));
+  } else {
+    if (p->kry_owned_bytes < need) {
+      if (p->kry_owned) cudaFree(p->kry_owned);
+      p->kry_owned = nullptr;
+      p->kry_owned_bytes = 0;
+      CU(cudaMalloc(&p->kry_owned, need));
+      p->kry_owned_bytes = need;
+    }
+    ws = (double*)p->kry_owned;
+  }
+  int ni = 0, inf = 0;
+  int rc = (o->side == MPBP_SIDE_LEFT) ? gmres_left(p, b, x, o, ws, hist, hist_cap, &ni, &inf)
+                                       : gmres_right(p, b, x, o, ws, hist, hist_cap, &ni, &inf);
+  if (n_iters) *n_iters = ni;
+  if (info) *info = inf;
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(p->st));
+  return 0;
+}
+
+extern "C" int mpbp_gmres(mpbp_plan* p, const double* b, double* x, const mpbp_gmres_opts* o, double* hist, int hist_cap,
+                          int* n_iters, int* info, void* stream) {
+  ENTER(p, stream);
+  if (!b || !x || b == x) return set_err(MPBP_E_ARG, "gmres: bad pointers");
+  return gmres_dispatch(p, b, x, o, hist, hist_cap, n_iters, info);
+}
+extern "C" int mpbp_gmres_host(mpbp_plan* p, const double* b_host, double* x_host, const mpbp_gmres_opts* o, double* hist,
+                               int hist_cap, int* n_iters, int* info, void* stream) {
+  ENTER(p, stream);
+  if (!b_host || !x_host) return set_err(MPBP_E_ARG, "gmres_host: bad pointers");
+  RET(ensure_hostbuf(p));
+  const size_t bytes = 5 * p->lev[0].fs() * sizeof(double);
+  CU(cudaMemcpyAsync(p->hostbuf_dev[0], b_host, bytes, cudaMemcpyHostToDevice, p->st));
+  if (o && o->x0_nonzero) CU(cudaMemcpyAsync(p->hostbuf_dev[1], x_host, bytes, cudaMemcpyHostToDevice, p->st));
+  RET(gmres_dispatch(p, p->hostbuf_dev[0], p->hostbuf_dev[1], o, hist, hist_cap, n_iters, info));
+  CU(cudaMemcpyAsync(x_host, p->hostbuf_dev[1], bytes, cudaMemcpyDeviceToHost, p->st));
+  CU(cudaStreamSynchronize(p->st));
+  return 0;
+}

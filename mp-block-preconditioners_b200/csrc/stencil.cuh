@@ -1,0 +1,532 @@
+// Matrix-free MAC-grid stencil kernels (fp64, sm_100a) for the two-phase Stokes hot path.
+//
+// All operators are written in flux (stress-divergence) form, which is algebraically the dense
+// matrices of preconditioner.py:86-349 ("flux form"):
+//   Q = theta      * [(u[r,c+1]-u[r,c]) + (v[r+1,c]-v[r,c])]     at cell centres
+//   T = theta_node * [(u[r-1,c]-u[r,c]) + (v[r,c]-v[r,c-1])]     at cell corners (top-left of (r,c))
+//   (L u)_u = (Q[r,c]-Q[r,c-1]) + (T[r,c]-T[r+1,c])              preconditioner.py:127-179
+//   (L u)_v = (T[r,c+1]-T[r,c]) + (Q[r,c]-Q[r-1,c])              preconditioner.py:242-295
+//
+// Thread mapping ("column marching"): one lane owns one grid column and walks down a strip of rows
+// keeping a 3-row window in registers; horizontal neighbours are exchanged with warp shuffles.
+// A warp spans 32 columns and produces 30 (lanes 1..30); lanes 0/31 are read-only halo lanes, so
+// no shared memory and no block barrier is needed.  Rows above/below the slab come through the
+// `top`/`bot` halo pointers (periodic wrap on one GPU, neighbour rows after a halo exchange).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mpbp {
+
+constexpr int kWarpCols = 30;   // output columns per warp
+constexpr int kBlockWarps = 4;  // warps per block, side by side in x
+constexpr int kBlockThreads = 32 * kBlockWarps;
+constexpr unsigned kFull = 0xffffffffu;
+
+struct Phys {
+  double xi, c, d_u;
+  double kap_n, kap_s;  // d_u*eta/h^2
+  double dp_h;          // d_p/h
+  double ddiv_h;        // d_div/h
+  double inv_h;         // 1/h
+  double dp_h2;         // d_p/h^2
+  int mass_mode;        // 1: analytic separable face tables (level 0), 0: two-cell face average
+  const double *sxf, *sxc, *syf, *syc;
+};
+
+// input vector view: field k at x + k*fs; halo rows (row -1 / row `rows`) at top + k*hs, bot + k*hs
+struct VecIn {
+  const double* x;
+  const double* top;
+  const double* bot;
+  size_t fs, hs;
+};
+
+struct Geo {
+  int n;     // columns (= global grid size of the level)
+  int rows;  // local rows of the slab
+  int row0;  // global index of local row 0
+  int rs;    // rows per strip (gridDim.y strips)
+};
+
+__device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(kFull, v, 1); }
+__device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(kFull, v, 1); }
+
+__device__ __forceinline__ const double* row_ptr(const VecIn& v, int k, int r, int rows, int n) {
+  if (r < 0) return v.top + k * v.hs;
+  if (r >= rows) return v.bot + k * v.hs;
+  return v.x + k * v.fs + (size_t)r * n;
+}
+
+// theta is stored padded: row r (r in [-1, rows]) at th + (r+1)*n
+__device__ __forceinline__ const double* th_row(const double* th, int r, int n) { return th + (size_t)(r + 1) * n; }
+
+__device__ __forceinline__ double fast_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+struct LaneGeom {
+  int cc;       // wrapped column this lane reads
+  int j;        // unwrapped output column
+  bool store;   // lane writes output
+  bool alive;   // warp has at least one output column
+};
+
+__device__ __forceinline__ LaneGeom lane_geom(int n) {
+  LaneGeom g;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int j0 = (blockIdx.x * kBlockWarps + warp) * kWarpCols;
+  g.alive = j0 < n;
+  g.j = j0 + lane - 1;
+  int cc = g.j % n;
+  if (cc < 0) cc += n;
+  g.cc = cc;
+  g.store = (lane >= 1) && (lane <= kWarpCols) && (g.j < n);
+  return g;
+}
+
+// ------------------------------------------------------------------------------------------
+// Velocity-block / full-system kernel.
+//   MODE 0: y = Op x            (Op = F, or A when WITH_P)         K1 / K2
+//   MODE 1: y = b - F x                                             K2 residual
+//   MODE 2: y = x + omega * (b - F x) / diag(F)                     K3, solve.py:149-159 (damped)
+// ------------------------------------------------------------------------------------------
+template <int MODE, bool WITH_P>
+__global__ void __launch_bounds__(kBlockThreads) k_stokes(VecIn xin, const double* __restrict__ th,
+                                                          const double* __restrict__ b, double* __restrict__ y,
+                                                          Geo g, Phys ph, double omega) {
+  const LaneGeom lg = lane_geom(g.n);
+  if (!lg.alive) return;
+  const int n = g.n, rows = g.rows, c = lg.cc;
+  const int r0 = blockIdx.y * g.rs;
+  const int r1 = min(r0 + g.rs, rows);
+  if (r0 >= rows) return;
+
+  double sxf = 0.0, sxc = 0.0;
+  if (ph.mass_mode) {
+    sxf = ph.sxf[c];
+    sxc = ph.sxc[c];
+  }
+
+  // ---- prologue: rows r0-1 and r0 ----
+  double th_m = th_row(th, r0 - 1, n)[c];
+  double th_c = th_row(th, r0, n)[c];
+  double un_m = row_ptr(xin, 0, r0 - 1, rows, n)[c], vn_m = row_ptr(xin, 1, r0 - 1, rows, n)[c];
+  double us_m = row_ptr(xin, 2, r0 - 1, rows, n)[c], vs_m = row_ptr(xin, 3, r0 - 1, rows, n)[c];
+  double un_c = row_ptr(xin, 0, r0, rows, n)[c], vn_c = row_ptr(xin, 1, r0, rows, n)[c];
+  double us_c = row_ptr(xin, 2, r0, rows, n)[c], vs_c = row_ptr(xin, 3, r0, rows, n)[c];
+  double p_m = 0.0, p_c = 0.0;
+  if (WITH_P) {
+    p_m = row_ptr(xin, 4, r0 - 1, rows, n)[c];
+    p_c = row_ptr(xin, 4, r0, rows, n)[c];
+  }
+  const double a_m = th_m + shfl_up1(th_m);
+  double a_c = th_c + shfl_up1(th_c);
+  double node_c = 0.25 * (a_c + a_m);
+  double Tn_c = node_c * ((un_m - un_c) + (vn_c - shfl_up1(vn_c)));
+  double Ts_c = (1.0 - node_c) * ((us_m - us_c) + (vs_c - shfl_up1(vs_c)));
+  double Qn_m = th_m * ((shfl_dn1(un_m) - un_m) + (vn_c - vn_m));
+  double Qs_m = (1.0 - th_m) * ((shfl_dn1(us_m) - us_m) + (vs_c - vs_m));
+  double fv_c = 0.5 * (th_c + th_m);
+  double Vsum_c = vs_c + fv_c * (vn_c - vs_c);
+
+  // next row (r0+1) raw values, software-prefetched one row ahead of use
+  double th_p = th_row(th, r0 + 1, n)[c];
+  double un_p = row_ptr(xin, 0, r0 + 1, rows, n)[c], vn_p = row_ptr(xin, 1, r0 + 1, rows, n)[c];
+  double us_p = row_ptr(xin, 2, r0 + 1, rows, n)[c], vs_p = row_ptr(xin, 3, r0 + 1, rows, n)[c];
+  double p_p = 0.0;
+  if (WITH_P) p_p = row_ptr(xin, 4, r0 + 1, rows, n)[c];
+
+  const size_t fs = xin.fs;
+#pragma unroll 2
+  for (int r = r0; r < r1; ++r) {
+    // prefetch row r+2 (clamped to r1: the last prefetch is unused but stays in bounds of the halo)
+    const int rq = min(r + 2, r1);
+    const double th_q = th_row(th, rq, n)[c];
+    const double un_q = row_ptr(xin, 0, rq, rows, n)[c], vn_q = row_ptr(xin, 1, rq, rows, n)[c];
+    const double us_q = row_ptr(xin, 2, rq, rows, n)[c], vs_q = row_ptr(xin, 3, rq, rows, n)[c];
+    double p_q = 0.0;
+    if (WITH_P) p_q = row_ptr(xin, 4, rq, rows, n)[c];
+    double bn_u = 0.0, bn_v = 0.0, bs_u = 0.0, bs_v = 0.0;
+    const size_t off = (size_t)r * n + c;
+    if (MODE != 0) {
+      bn_u = b[off];
+      bn_v = b[off + fs];
+      bs_u = b[off + 2 * fs];
+      bs_v = b[off + 3 * fs];
+    }
+
+    const double a_p = th_p + shfl_up1(th_p);
+    const double node_p = 0.25 * (a_p + a_c);
+    const double Tn_p = node_p * ((un_c - un_p) + (vn_p - shfl_up1(vn_p)));
+    const double Ts_p = (1.0 - node_p) * ((us_c - us_p) + (vs_p - shfl_up1(vs_p)));
+    const double Qn_c = th_c * ((shfl_dn1(un_c) - un_c) + (vn_p - vn_c));
+    const double Qs_c = (1.0 - th_c) * ((shfl_dn1(us_c) - us_c) + (vs_p - vs_c));
+    const double Lu_n = (Qn_c - shfl_up1(Qn_c)) + (Tn_c - Tn_p);
+    const double Lu_s = (Qs_c - shfl_up1(Qs_c)) + (Ts_c - Ts_p);
+    const double Lv_n = (shfl_dn1(Tn_c) - Tn_c) + (Qn_c - Qn_m);
+    const double Lv_s = (shfl_dn1(Ts_c) - Ts_c) + (Qs_c - Qs_m);
+
+    const double fu_c = 0.5 * a_c;
+    double mu, mv;
+    if (ph.mass_mode) {
+      const int gr = g.row0 + r;
+      mu = 0.25 * sxf * ph.syc[gr] + 0.5;  // thn(-(r+1/2)h, c h), preconditioner.py:325
+      mv = 0.25 * sxc * ph.syf[gr] + 0.5;  // thn(-r h, (c+1/2)h), preconditioner.py:326
+    } else {
+      mu = fu_c;
+      mv = fv_c;
+    }
+    const double dXu = ph.d_u * (ph.xi * fu_c * (1.0 - fu_c));  // preconditioner.py:124
+    const double dXv = ph.d_u * (ph.xi * fv_c * (1.0 - fv_c));  // preconditioner.py:125
+    const double du = un_c - us_c, dv = vn_c - vs_c;
+    const double cmu = ph.c * mu, cmv = ph.c * mv;
+    double y_un = cmu * un_c - dXu * du + ph.kap_n * Lu_n;
+    double y_us = (ph.c - cmu) * us_c + dXu * du + ph.kap_s * Lu_s;
+    double y_vn = cmv * vn_c - dXv * dv + ph.kap_n * Lv_n;
+    double y_vs = (ph.c - cmv) * vs_c + dXv * dv + ph.kap_s * Lv_s;
+    const double fv_p = 0.5 * (th_p + th_c);
+    const double Vsum_p = vs_p + fv_p * (vn_p - vs_p);
+    double y_p = 0.0;
+    if (WITH_P) {
+      const double gx = ph.dp_h * (p_c - shfl_up1(p_c));  // preconditioner.py:204-210
+      const double gy = ph.dp_h * (p_m - p_c);            // preconditioner.py:213-219
+      y_un += fu_c * gx;
+      y_us += (1.0 - fu_c) * gx;
+      y_vn += fv_c * gy;
+      y_vs += (1.0 - fv_c) * gy;
+      const double Usum_c = us_c + fu_c * du;
+      y_p = ph.ddiv_h * ((shfl_dn1(Usum_c) - Usum_c) + (Vsum_c - Vsum_p));  // preconditioner.py:221-238, :312
+    }
+    if (MODE == 1) {
+      y_un = bn_u - y_un;
+      y_vn = bn_v - y_vn;
+      y_us = bs_u - y_us;
+      y_vs = bs_v - y_vs;
+    }
+    if (MODE == 2) {
+      const double node_e = shfl_dn1(node_c);
+      const double su = a_c + node_c + node_p;           // tE+tW+nN+nS, preconditioner.py:127
+      const double sv = th_m + th_c + node_c + node_e;   // tN+tC+nL+nR, preconditioner.py:242
+      const double d_un = cmu - dXu - ph.kap_n * su;
+      const double d_us = (ph.c - cmu) - dXu - ph.kap_s * (4.0 - su);
+      const double d_vn = cmv - dXv - ph.kap_n * sv;
+      const double d_vs = (ph.c - cmv) - dXv - ph.kap_s * (4.0 - sv);
+      y_un = un_c + omega * (bn_u - y_un) * fast_rcp(d_un);
+      y_us = us_c + omega * (bs_u - y_us) * fast_rcp(d_us);
+      y_vn = vn_c + omega * (bn_v - y_vn) * fast_rcp(d_vn);
+      y_vs = vs_c + omega * (bs_v - y_vs) * fast_rcp(d_vs);
+    }
+    if (lg.store) {
+      y[off] = y_un;
+      y[off + fs] = y_vn;
+      y[off + 2 * fs] = y_us;
+      y[off + 3 * fs] = y_vs;
+      if (WITH_P && MODE == 0) y[off + 4 * fs] = y_p;
+    }
+    // rotate the window
+    th_m = th_c; th_c = th_p; th_p = th_q;
+    a_c = a_p; node_c = node_p;
+    un_c = un_p; vn_c = vn_p; us_c = us_p; vs_c = vs_p;
+    un_p = un_q; vn_p = vn_q; us_p = us_q; vs_p = vs_q;
+    p_m = p_c; p_c = p_p; p_p = p_q;
+    Tn_c = Tn_p; Ts_c = Ts_p; Qn_m = Qn_c; Qs_m = Qs_c;
+    fv_c = fv_p; Vsum_c = Vsum_p;
+  }
+}
+
+// x = omega * b / diag(F): first Jacobi sweep from a zero initial guess (solve.py:149-159 with x=0)
+__global__ void __launch_bounds__(kBlockThreads) k_jacobi0_F(const double* __restrict__ th, const double* __restrict__ b,
+                                                             double* __restrict__ y, size_t fs, Geo g, Phys ph,
+                                                             double omega) {
+  const LaneGeom lg = lane_geom(g.n);
+  if (!lg.alive) return;
+  const int n = g.n, rows = g.rows, c = lg.cc;
+  const int r0 = blockIdx.y * g.rs;
+  const int r1 = min(r0 + g.rs, rows);
+  if (r0 >= rows) return;
+  double sxf = 0.0, sxc = 0.0;
+  if (ph.mass_mode) {
+    sxf = ph.sxf[c];
+    sxc = ph.sxc[c];
+  }
+  double th_m = th_row(th, r0 - 1, n)[c];
+  double th_c = th_row(th, r0, n)[c];
+  const double a_m = th_m + shfl_up1(th_m);
+  double a_c = th_c + shfl_up1(th_c);
+  double node_c = 0.25 * (a_c + a_m);
+  for (int r = r0; r < r1; ++r) {
+    const double th_p = th_row(th, r + 1, n)[c];
+    const double a_p = th_p + shfl_up1(th_p);
+    const double node_p = 0.25 * (a_p + a_c);
+    const double node_e = shfl_dn1(node_c);
+    const double fu_c = 0.5 * a_c, fv_c = 0.5 * (th_c + th_m);
+    double mu, mv;
+    if (ph.mass_mode) {
+      const int gr = g.row0 + r;
+      mu = 0.25 * sxf * ph.syc[gr] + 0.5;
+      mv = 0.25 * sxc * ph.syf[gr] + 0.5;
+    } else {
+      mu = fu_c;
+      mv = fv_c;
+    }
+    const double dXu = ph.d_u * (ph.xi * fu_c * (1.0 - fu_c));
+    const double dXv = ph.d_u * (ph.xi * fv_c * (1.0 - fv_c));
+    const double cmu = ph.c * mu, cmv = ph.c * mv;
+    const double su = a_c + node_c + node_p;
+    const double sv = th_m + th_c + node_c + node_e;
+    const double d_un = cmu - dXu - ph.kap_n * su;
+    const double d_us = (ph.c - cmu) - dXu - ph.kap_s * (4.0 - su);
+    const double d_vn = cmv - dXv - ph.kap_n * sv;
+    const double d_vs = (ph.c - cmv) - dXv - ph.kap_s * (4.0 - sv);
+    if (lg.store) {
+      const size_t off = (size_t)r * n + c;
+      y[off] = omega * b[off] * fast_rcp(d_un);
+      y[off + fs] = omega * b[off + fs] * fast_rcp(d_vn);
+      y[off + 2 * fs] = omega * b[off + 2 * fs] * fast_rcp(d_us);
+      y[off + 3 * fs] = omega * b[off + 3 * fs] * fast_rcp(d_vs);
+    }
+    th_m = th_c; th_c = th_p; a_c = a_p; node_c = node_p;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Pressure-Poisson operator GtG = -D G (solve.py:246-247): 5-point, face weights wu = fu_n^2+fu_s^2.
+//   MODE 0: y = GtG p ; 1: y = b - GtG p ; 2: y = p + omega (b - GtG p)/diag ; 3: y = omega b/diag
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kBlockThreads) k_poisson(VecIn pin, const double* __restrict__ th,
+                                                           const double* __restrict__ b, double* __restrict__ y,
+                                                           Geo g, Phys ph, double omega) {
+  const LaneGeom lg = lane_geom(g.n);
+  if (!lg.alive) return;
+  const int n = g.n, rows = g.rows, c = lg.cc;
+  const int r0 = blockIdx.y * g.rs;
+  const int r1 = min(r0 + g.rs, rows);
+  if (r0 >= rows) return;
+  double th_m = th_row(th, r0 - 1, n)[c];
+  double th_c = th_row(th, r0, n)[c];
+  double p_m = 0.0, p_c = 0.0;
+  if (MODE != 3) {
+    p_m = row_ptr(pin, 0, r0 - 1, rows, n)[c];
+    p_c = row_ptr(pin, 0, r0, rows, n)[c];
+  }
+  double fv = 0.5 * (th_c + th_m);
+  double wv_c = fv * fv + (1.0 - fv) * (1.0 - fv);
+  double Hy_c = wv_c * (p_m - p_c);
+#pragma unroll 2
+  for (int r = r0; r < r1; ++r) {
+    const double th_p = th_row(th, r + 1, n)[c];
+    double p_p = 0.0;
+    if (MODE != 3) p_p = row_ptr(pin, 0, r + 1, rows, n)[c];
+    const double fu = 0.5 * (th_c + shfl_up1(th_c));
+    const double wu = fu * fu + (1.0 - fu) * (1.0 - fu);
+    const double Hx = wu * (p_c - shfl_up1(p_c));
+    fv = 0.5 * (th_p + th_c);
+    const double wv_p = fv * fv + (1.0 - fv) * (1.0 - fv);
+    const double Hy_p = wv_p * (p_c - p_p);
+    double out = -ph.dp_h2 * ((shfl_dn1(Hx) - Hx) + (Hy_c - Hy_p));
+    const size_t off = (size_t)r * n + c;
+    if (MODE == 1) out = b[off] - out;
+    if (MODE == 2 || MODE == 3) {
+      const double dg = ph.dp_h2 * (shfl_dn1(wu) + wu + wv_c + wv_p);
+      const double rinv = fast_rcp(dg);
+      if (MODE == 2) out = p_c + omega * (b[off] - out) * rinv;
+      else out = omega * b[off] * rinv;
+    }
+    if (lg.store) y[off] = out;
+    th_m = th_c; th_c = th_p; p_m = p_c; p_c = p_p; wv_c = wv_p; Hy_c = Hy_p;
+  }
+}
+
+// r = D w (+ add): un-negated divergence of both phases (preconditioner.py:221-238, :311; solve.py:259)
+__global__ void __launch_bounds__(kBlockThreads) k_div(VecIn win, const double* __restrict__ th,
+                                                       const double* __restrict__ add, double* __restrict__ y, Geo g,
+                                                       Phys ph) {
+  const LaneGeom lg = lane_geom(g.n);
+  if (!lg.alive) return;
+  const int n = g.n, rows = g.rows, c = lg.cc;
+  const int r0 = blockIdx.y * g.rs;
+  const int r1 = min(r0 + g.rs, rows);
+  if (r0 >= rows) return;
+  double th_m = th_row(th, r0 - 1, n)[c];
+  double th_c = th_row(th, r0, n)[c];
+  double vn_c = row_ptr(win, 1, r0, rows, n)[c], vs_c = row_ptr(win, 3, r0, rows, n)[c];
+  double fv = 0.5 * (th_c + th_m);
+  double Vsum_c = vs_c + fv * (vn_c - vs_c);
+#pragma unroll 2
+  for (int r = r0; r < r1; ++r) {
+    const double th_p = th_row(th, r + 1, n)[c];
+    const double vn_p = row_ptr(win, 1, r + 1, rows, n)[c], vs_p = row_ptr(win, 3, r + 1, rows, n)[c];
+    const double un_c = row_ptr(win, 0, r, rows, n)[c], us_c = row_ptr(win, 2, r, rows, n)[c];
+    const double fu = 0.5 * (th_c + shfl_up1(th_c));
+    const double Usum = us_c + fu * (un_c - us_c);
+    fv = 0.5 * (th_p + th_c);
+    const double Vsum_p = vs_p + fv * (vn_p - vs_p);
+    double out = ph.inv_h * ((shfl_dn1(Usum) - Usum) + (Vsum_c - Vsum_p));
+    const size_t off = (size_t)r * n + c;
+    if (add != nullptr) out += add[off];
+    if (lg.store) y[off] = out;
+    th_m = th_c; th_c = th_p; Vsum_c = Vsum_p;
+  }
+}
+
+// y = G p for both phases (preconditioner.py:203-219, :313; solve.py:273)
+__global__ void __launch_bounds__(kBlockThreads) k_grad(VecIn pin, const double* __restrict__ th,
+                                                        double* __restrict__ y, size_t fs, Geo g, Phys ph) {
+  const LaneGeom lg = lane_geom(g.n);
+  if (!lg.alive) return;
+  const int n = g.n, rows = g.rows, c = lg.cc;
+  const int r0 = blockIdx.y * g.rs;
+  const int r1 = min(r0 + g.rs, rows);
+  if (r0 >= rows) return;
+  double th_m = th_row(th, r0 - 1, n)[c];
+  double p_m = row_ptr(pin, 0, r0 - 1, rows, n)[c];
+#pragma unroll 2
+  for (int r = r0; r < r1; ++r) {
+    const double th_c = th_row(th, r, n)[c];
+    const double p_c = row_ptr(pin, 0, r, rows, n)[c];
+    const double fu = 0.5 * (th_c + shfl_up1(th_c));
+    const double fv = 0.5 * (th_c + th_m);
+    const double gx = ph.dp_h * (p_c - shfl_up1(p_c));
+    const double gy = ph.dp_h * (p_m - p_c);
+    if (lg.store) {
+      const size_t off = (size_t)r * n + c;
+      y[off] = fu * gx;
+      y[off + fs] = fv * gy;
+      y[off + 2 * fs] = (1.0 - fu) * gx;
+      y[off + 3 * fs] = (1.0 - fv) * gy;
+    }
+    th_m = th_c; p_m = p_c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// grid transfers (thread per output cell; coarse cell (R,C) covers fine (2R..2R+1, 2C..2C+1))
+// ------------------------------------------------------------------------------------------
+// full weighting of the four face fields: u: (1/4,1/2,1/4) over columns x (1/2,1/2) over rows; v transposed
+__global__ void k_restrict_F(VecIn fin, double* __restrict__ yc, int nf, int rows_f) {
+  const int nc = nf >> 1, rows_c = rows_f >> 1;
+  const int C = blockIdx.x * blockDim.x + threadIdx.x;
+  const int R = blockIdx.y;
+  if (C >= nc || R >= rows_c) return;
+  const size_t fsc = (size_t)rows_c * nc;
+  const int c0 = 2 * C, cm = (c0 == 0) ? nf - 1 : c0 - 1, cp = c0 + 1;
+  const int ra = 2 * R, rb = 2 * R + 1;
+#pragma unroll
+  for (int ph = 0; ph < 2; ++ph) {
+    const double* ua = row_ptr(fin, 2 * ph, ra, rows_f, nf);
+    const double* ub = row_ptr(fin, 2 * ph, rb, rows_f, nf);
+    const double um = 0.5 * (ua[cm] + ub[cm]), u0 = 0.5 * (ua[c0] + ub[c0]), up = 0.5 * (ua[cp] + ub[cp]);
+    yc[(2 * ph) * fsc + (size_t)R * nc + C] = 0.25 * um + 0.5 * u0 + 0.25 * up;
+    const double* vm = row_ptr(fin, 2 * ph + 1, ra - 1, rows_f, nf);
+    const double* v0 = row_ptr(fin, 2 * ph + 1, ra, rows_f, nf);
+    const double* vp = row_ptr(fin, 2 * ph + 1, rb, rows_f, nf);
+    const double wm = 0.5 * (vm[c0] + vm[cp]), w0 = 0.5 * (v0[c0] + v0[cp]), wp = 0.5 * (vp[c0] + vp[cp]);
+    yc[(2 * ph + 1) * fsc + (size_t)R * nc + C] = 0.25 * wm + 0.5 * w0 + 0.25 * wp;
+  }
+}
+
+// x_f += P x_c, P = 4 R^T: u linear in x / constant in y, v linear in y / constant in x
+__global__ void k_prolong_add_F(VecIn cin, double* __restrict__ xf, int nf, int rows_f) {
+  const int nc = nf >> 1, rows_c = rows_f >> 1;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c >= nf || r >= rows_f) return;
+  const size_t fsf = (size_t)rows_f * nf;
+  const int C = c >> 1, R = r >> 1;
+  const int Cp = (C + 1 == nc) ? 0 : C + 1;
+#pragma unroll
+  for (int ph = 0; ph < 2; ++ph) {
+    const double* uc = row_ptr(cin, 2 * ph, R, rows_c, nc);
+    const double eu = (c & 1) ? 0.5 * (uc[C] + uc[Cp]) : uc[C];
+    xf[(2 * ph) * fsf + (size_t)r * nf + c] += eu;
+    const double* v0 = row_ptr(cin, 2 * ph + 1, R, rows_c, nc);
+    double ev = v0[C];
+    if (r & 1) ev = 0.5 * (ev + row_ptr(cin, 2 * ph + 1, R + 1, rows_c, nc)[C]);
+    xf[(2 * ph + 1) * fsf + (size_t)r * nf + c] += ev;
+  }
+}
+
+// 4-cell average of a cell-centred field
+__global__ void k_restrict_P(const double* __restrict__ f, double* __restrict__ yc, int nf, int rows_f) {
+  const int nc = nf >> 1, rows_c = rows_f >> 1;
+  const int C = blockIdx.x * blockDim.x + threadIdx.x;
+  const int R = blockIdx.y;
+  if (C >= nc || R >= rows_c) return;
+  const double* a = f + (size_t)(2 * R) * nf + 2 * C;
+  const double* bq = a + nf;
+  yc[(size_t)R * nc + C] = 0.25 * ((a[0] + a[1]) + (bq[0] + bq[1]));
+}
+
+// x_f += piecewise-constant prolongation of x_c
+__global__ void k_prolong_add_P(const double* __restrict__ xc, double* __restrict__ xf, int nf, int rows_f) {
+  const int nc = nf >> 1;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c >= nf || r >= rows_f) return;
+  xf[(size_t)r * nf + c] += xc[(size_t)(r >> 1) * nc + (c >> 1)];
+}
+
+// y = M x for the coarsest-level dense (pseudo-)inverse; Mt is column-major (Mt[k*m+i] = M[i][k])
+__global__ void k_dense_matvec(const double* __restrict__ Mt, const double* __restrict__ x, double* __restrict__ y,
+                               int m) {
+  extern __shared__ double sx[];
+  for (int i = threadIdx.x; i < m; i += blockDim.x) sx[i] = x[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    double acc = 0.0;
+    for (int k = 0; k < m; ++k) acc = fma(Mt[(size_t)k * m + i], sx[k], acc);
+    y[i] = acc;
+  }
+}
+
+// manufactured solution and right-hand side of solve.main (solve.py:52-78 via utils.py:159-210)
+__global__ void k_fill_manufactured(double* __restrict__ u_vec, double* __restrict__ b_vec, int n, int rows, int row0,
+                                    double c, double d, double xi, double etan, double etas, double b_p_sign) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (col >= n || r >= rows) return;
+  const double PI = 3.141592653589793;
+  const double h = 1.0 / n, nu = 1.0;
+  const int gr = row0 + r;
+  const size_t fs = (size_t)rows * n, off = (size_t)r * n + col;
+  const double yu = -(gr + 0.5) * h, xu = col * h;          // utils.py:187
+  const double yv = -gr * h, xv = (col + 0.5) * h;          // utils.py:188
+  const double yp = -(gr + 0.5) * h, xp = (col + 0.5) * h;  // utils.py:193
+  {
+    const double sx = sin(2 * PI * xu), cy = cos(2 * PI * yu), sy = sin(2 * PI * yu);
+    const double ux = sx * cy;  // solve.py:52
+    const double common = 2 * nu * sx * sy;
+    const double s2 = sx * sx * sy * sy;
+    const double bn = (cy * sx * (4 * c * nu - 4 * d * (8 * etan * nu * PI * PI + xi) +
+                                  (c - 16 * d * etan * PI * PI) * common + d * xi * s2)) / (8 * nu);  // solve.py:72
+    const double bs = (cy * sx * (-4 * c * nu + 4 * d * (8 * etas * nu * PI * PI + xi) +
+                                  (c - 16 * d * etas * PI * PI) * common - d * xi * s2)) / (8 * nu);  // solve.py:75
+    if (u_vec) { u_vec[off] = ux; u_vec[off + 2 * fs] = -ux; }
+    if (b_vec) { b_vec[off] = bn; b_vec[off + 2 * fs] = bs; }
+  }
+  {
+    const double cx = cos(2 * PI * xv), sx = sin(2 * PI * xv), sy = sin(2 * PI * yv);
+    const double uy = cx * sy;  // solve.py:53
+    const double common = 2 * nu * sx * sy;
+    const double s2 = sx * sx * sy * sy;
+    const double bn = (cx * sy * (4 * c * nu - 4 * d * (8 * etan * nu * PI * PI + xi) +
+                                  (c - 16 * d * etan * PI * PI) * common + d * xi * s2)) / (8 * nu);  // solve.py:73
+    const double bs = (cx * sy * (-4 * c * nu + 4 * d * (8 * etas * nu * PI * PI + xi) +
+                                  (c - 16 * d * etas * PI * PI) * common - d * xi * s2)) / (8 * nu);  // solve.py:76
+    if (u_vec) { u_vec[off + fs] = uy; u_vec[off + 3 * fs] = -uy; }
+    if (b_vec) { b_vec[off + fs] = bn; b_vec[off + 3 * fs] = bs; }
+  }
+  if (u_vec) u_vec[off + 4 * fs] = 0.0;                                                    // solve.py:58
+  if (b_vec) b_vec[off + 4 * fs] = b_p_sign * PI * sin(4 * PI * xp) * sin(4 * PI * yp);  // solve.py:78
+}
+
+}  // namespace mpbp

@@ -1,0 +1,363 @@
+"""Parity of the CUDA path (through the Python host -> C ABI -> kernels) against the CPU oracle and
+the golden fixtures generated from the reference's own code.  fp64; tolerances are stated per test."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import mpbp_oracle as O
+from conftest import golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+OPS_FIXTURES = ["ops_n4_eta1.npz", "ops_n8_eta100.npz", "ops_n16_eta100.npz", "ops_n12_eta3.npz", "ops_n16_eta10000.npz"]
+
+
+def _bp(mp, params, **kw):
+    n, xi, eta_n, eta_s, c, d = params
+    return mp.MultiphaseBlockPreconditioner(int(n), xi, eta_n, eta_s, **kw), int(n), c, d
+
+
+@pytest.mark.parametrize("fx", OPS_FIXTURES)
+def test_operators_vs_reference_golden(mp, fx):
+    """A, F, D, G, Gt_G, Gt_F_G applied to a seeded vector vs the reference's dense matmuls. tol 1e-13 rel."""
+    g = golden(fx)
+    bp, n, c, d = _bp(mp, g["params"])
+    N = n * n
+    A, S, F, D, G = bp.get_big_A_matrix(c=c, d_u=d)
+    GtG, GtFG, _, _ = bp.derived_operators(c=c, d_u=d)
+    x = g["x"]
+    assert A.shape == (5 * N, 5 * N) and F.shape == (4 * N, 4 * N) and D.shape == (N, 4 * N) and G.shape == (4 * N, N)
+    assert relerr(A @ x, g["Ax"]) < 1e-13
+    assert relerr(F @ x[:4 * N], g["Fx"]) < 1e-13
+    assert relerr(D @ x[:4 * N], g["Dx"]) < 1e-13
+    assert relerr(G @ x[4 * N:], g["Gp"]) < 1e-13
+    assert relerr(GtG @ x[4 * N:], g["GtGp"]) < 1e-13
+    assert relerr(GtFG @ x[4 * N:], g["GtFGp"]) < 1e-12
+    assert relerr(A @ g["u_vec"], g["Au"]) < 1e-13
+    assert relerr(A @ g["b_vec"], g["Ab"]) < 1e-13
+
+
+@pytest.mark.parametrize("fx", OPS_FIXTURES[:3])
+def test_dense_matrix_entries_vs_reference(mp, fx):
+    """Every entry of A (operator applied to the identity) vs the reference's dense A."""
+    g = golden(fx)
+    bp, n, c, d = _bp(mp, g["params"])
+    A = bp.get_big_A_matrix(c=c, d_u=d)[0]
+    ref = sp.csr_matrix((g["A_data"], g["A_indices"], g["A_indptr"]), shape=tuple(g["A_shape"])).toarray()
+    got = A.toarray()
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-14
+    assert abs(np.linalg.norm(got) - float(g["normA"])) / float(g["normA"]) < 1e-13
+
+
+@pytest.mark.parametrize("fx", OPS_FIXTURES)
+def test_manufactured_vectors(mp, fx):
+    """solve.main's (u_vec, b_vec): host mirror and device kernel vs the reference's fill loop."""
+    g = golden(fx)
+    n, xi, eta_n, eta_s, c, d = g["params"]
+    A, b_vec, u_vec = mp.main(n=int(n), c=c, d=d, xi=xi, eta_n=eta_n, eta_s=eta_s)
+    assert relerr(b_vec, g["b_vec"]) < 1e-13 and relerr(u_vec, g["u_vec"]) < 1e-14
+    A, b_dev, u_dev = mp.main(n=int(n), c=c, d=d, xi=xi, eta_n=eta_n, eta_s=eta_s, device_vectors=True)
+    assert relerr(b_dev.cpu().numpy(), g["b_vec"]) < 1e-13
+    assert relerr(u_dev.cpu().numpy(), g["u_vec"]) < 1e-13
+
+
+@pytest.mark.parametrize("fx", OPS_FIXTURES)
+def test_jacobi_vs_reference(mp, fx):
+    """solve.Jacobi run verbatim by the reference (3 undamped sweeps from 0) on F and Gt_G. tol 1e-12."""
+    g = golden(fx)
+    bp, n, c, d = _bp(mp, g["params"])
+    N = n * n
+    F = bp.get_big_A_matrix(c=c, d_u=d)[2]
+    GtG = bp.derived_operators(c=c, d_u=d)[0]
+    bF = g["x"][:4 * N]
+    assert relerr(mp.Jacobi(F, bF, 3, 0 * bF), g["jacF3"]) < 1e-12
+    assert relerr(mp.Jacobi(GtG, g["bP"], 3, 0 * g["bP"]), g["jacP3"]) < 1e-12
+
+
+@pytest.mark.parametrize("n", [4, 6, 8, 30, 33, 64, 100, 121, 256])
+def test_operators_vs_oracle_sizes(mp, n):
+    """Ragged sizes (not multiples of the 30-column warp tile, odd n, n smaller than a warp)."""
+    rng = np.random.default_rng(n)
+    xi, eta_n, eta_s, c, d, dp, dd = 0.8, 50.0, 2.0, 1.1, -0.9, 1.2, -1.1
+    ops = O.Operators(n, xi, eta_n, eta_s, c, d, dp, dd)
+    bp = mp.MultiphaseBlockPreconditioner(n, xi, eta_n, eta_s)
+    p = bp.plan(c, d, dp, dd, operators_only=True)
+    from mp_block_preconditioners_b200.preconditioner import (DivergenceOperator, GradientOperator, GtFGOperator,
+                                                              GtGOperator, SystemOperator, VelocityOperator)
+    N = n * n
+    x = rng.standard_normal(5 * N)
+    assert relerr(SystemOperator(p) @ x, ops.A @ x) < 1e-13
+    assert relerr(VelocityOperator(p) @ x[:4 * N], ops.F @ x[:4 * N]) < 1e-13
+    assert relerr(DivergenceOperator(p) @ x[:4 * N], ops.D @ x[:4 * N]) < 1e-13
+    assert relerr(GradientOperator(p) @ x[4 * N:], ops.G @ x[4 * N:]) < 1e-13
+    assert relerr(GtGOperator(p) @ x[4 * N:], ops.GtG @ x[4 * N:]) < 1e-13
+    assert relerr(GtFGOperator(p) @ x[4 * N:], ops.GtFG @ x[4 * N:]) < 1e-12
+
+
+@pytest.mark.parametrize("n,eta_n", [(16, 100.0), (32, 1.0), (64, 1e3), (48, 10.0)])
+@pytest.mark.parametrize("cheb", [False, True])
+def test_subsolvers_vs_oracle(mp, n, eta_n, cheb):
+    """One V-cycle, the configured F~^-1 / (GtG)~^-1 and damped Jacobi vs the oracle. tol 1e-10 rel."""
+    rng = np.random.default_rng(7)
+    xi, eta_s, c, d = 1.0, 1.0, 1.0, -1.0
+    sub = mp.SubSolver(kind="mg", F_cycles=3, P_cycles=2, cheb=cheb)
+    bp = mp.MultiphaseBlockPreconditioner(n, xi, eta_n, eta_s, sub_solver=sub)
+    p = bp.plan(c, d)
+    GtG, GtFG, Finv, Pinv = bp.derived_operators(c, d)
+    ops = O.Operators(n, xi, eta_n, eta_s, c, d)
+    N = n * n
+    bF = rng.standard_normal(4 * N)
+    bP = rng.standard_normal(N)
+    bP -= bP.mean()
+    for kF, kP in ((1, 1), (3, 2)):
+        cfgF = O.SubSolverConfig(kind="mg", cycles=kF, cheb=cheb)
+        cfgP = O.SubSolverConfig(kind="mg", cycles=kP, cheb=cheb)
+        mgF, mgP = O.Multigrid(ops, cfgF), O.Multigrid(ops, cfgP)
+        if kF == 1:
+            import torch
+            yF = p.call("mpbp_vcycle_F", bF, 4 * N, 4 * N)
+            yP = p.call("mpbp_vcycle_P", bP, N, N)
+            refF, refP = mgF._vcycle("F", 0, bF), mgP._vcycle("P", 0, bP)
+        else:
+            yF, yP = Finv @ bF, Pinv @ bP
+            refF, refP = mgF.solve("F", bF), mgP.solve("P", bP)
+        assert relerr(yF, refF) < 1e-10, (kF, relerr(yF, refF))
+        assert relerr(yP, refP) < 1e-10, (kP, relerr(yP, refP))
+    F = bp.get_big_A_matrix(c, d)[2]
+    assert relerr(mp.Jacobi(F, bF, 5, 0 * bF, omega=0.8), O.jacobi(ops.F, bF, 5, 0 * bF, 0.8)) < 1e-12
+    assert relerr(mp.Jacobi(GtG, bP, 5, 0 * bP, omega=0.8), O.jacobi(ops.GtG, bP, 5, 0 * bP, 0.8)) < 1e-12
+
+
+SOLVES = [("solve_mgcheb_n16_eta100.npz", dict(kind="mg", F_cycles=4, P_cycles=4, cheb=True)),
+          ("solve_mgplain_n16_eta100.npz", dict(kind="mg", F_cycles=2, P_cycles=2, cheb=False)),
+          ("solve_jacobi_n16_eta100.npz", dict(kind="jacobi", F_sweeps=20, P_sweeps=20, omega=0.8)),
+          ("solve_mgcheb_n32_eta1.npz", dict(kind="mg", F_cycles=4, P_cycles=4, cheb=True))]
+
+
+@pytest.mark.parametrize("fx,subkw", SOLVES)
+def test_precond_apply_vs_reference_closure(mp, fx, subkw):
+    """z = M v vs the reference's verbatim approx_schur_op closure (solve.py:257-277). tol 1e-9 rel."""
+    g = golden(fx)
+    bp, n, c, d = _bp(mp, g["params"], sub_solver=mp.SubSolver(**subkw))
+    M = bp.approx_schur_operator(c=c, d_u=d)
+    v = g["v"].copy()
+    z = M @ v
+    assert np.array_equal(v, g["v"])  # input untouched
+    assert z.shape == v.shape and z is not v
+    assert relerr(z, g["Mv"]) < 1e-9, relerr(z, g["Mv"])
+    assert relerr(M @ g["b_vec"], g["Mb"]) < 1e-9
+    assert relerr(M.matvec_host(v), g["Mv"]) < 1e-9
+
+
+def _hist_close(h, ref, rtol):
+    k = min(len(h), len(ref))
+    assert abs(len(h) - len(ref)) <= 1, (len(h), len(ref))
+    rel = np.abs(h[:k] - ref[:k]) / ref[:k]
+    return rel.max()
+
+
+@pytest.mark.parametrize("fx,subkw", SOLVES)
+def test_fgmres_history_vs_reference_run(mp, fx, subkw):
+    """Right-preconditioned FGMRES (solve.py:285) residual history, iterate and error norms vs the golden
+    run of the reference's solve_with_approx_schur_pc.  History within 1e-10 relative, count +-1."""
+    g = golden(fx)
+    n, xi, eta_n, eta_s, c, d = g["params"]
+    n = int(n)
+    u, info, hist = mp.solve_with_approx_schur_pc(n, xi, eta_n, eta_s, c, d, g["b_vec"], g["u_vec"],
+                                                  sub_solver=mp.SubSolver(**subkw), verbose=False)
+    assert info == 0
+    worst = _hist_close(hist, g["hist"], 1e-10)
+    assert worst < 1e-10, worst
+    assert relerr(u, g["x"]) < 1e-8
+    w = (1 / n) * (1 / n)
+    got = [mp.weighted_L1(u, g["u_vec"], w), mp.weighted_L2(u, g["u_vec"], w), mp.max_norm(u, g["u_vec"])]
+    assert np.allclose(got, g["err_norms"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("fx,subkw", SOLVES)
+@pytest.mark.parametrize("restart", [20, 150])
+def test_gmres_left_history_vs_scipy(mp, fx, subkw, restart):
+    """scipy.sparse.linalg.gmres semantics (left preconditioning): pr_norm history vs scipy run on the
+    reference's dense A with its verbatim preconditioner closure. 1e-10 relative, count +-1."""
+    g = golden(fx)
+    bp, n, c, d = _bp(mp, g["params"], sub_solver=mp.SubSolver(**subkw))
+    A = bp.get_big_A_matrix(c=c, d_u=d)[0]
+    M = bp.approx_schur_operator(c=c, d_u=d)
+    hist = []
+    x, info = mp.gmres(A, g["b_vec"], M=M, rtol=1e-8, restart=restart, maxiter=40, callback=hist.append,
+                       callback_type="pr_norm")
+    ref = g[f"scipy_hist_r{restart}"]
+    assert info == int(g[f"scipy_info_r{restart}"])
+    worst = _hist_close(np.array(hist), ref, 1e-10)
+    assert worst < 1e-10, worst
+    assert relerr(x, g[f"scipy_x_r{restart}"]) < 1e-7
+
+
+def test_true_residual_callback(mp):
+    """print_true_res_norm (solve.py:161-170) through the fgmres callback verification mode."""
+    g = golden("solve_mgcheb_n16_eta100.npz")
+    n, xi, eta_n, eta_s, c, d = g["params"]
+    sub = mp.SubSolver(kind="mg", F_cycles=4, P_cycles=4, cheb=True)
+    bp = mp.MultiphaseBlockPreconditioner(int(n), xi, eta_n, eta_s, sub_solver=sub)
+    A = bp.get_big_A_matrix(c=c, d_u=d)[0]
+    M = bp.approx_schur_operator(c=c, d_u=d)
+    out = []
+    x, info = mp.fgmres(A, g["b_vec"], M=M, tol=1e-8, maxiter=150, callback=mp.print_true_res_norm(A, g["b_vec"], out, verbose=False))
+    assert len(out) == len(g["true_res"])
+    assert np.allclose(out, g["true_res"], rtol=1e-6)
+
+
+def test_unpreconditioned_matches_oracle(mp):
+    """solve_without_pc (solve.py:202-208): M=None, 100 iterations, does not converge; history parity."""
+    n, xi, eta_n, eta_s, c, d = 16, 1.0, 100.0, 1.0, 1, -1
+    A, b_vec, u_vec = mp.main(n=n, c=c, d=d, xi=xi, eta_n=eta_n, eta_s=eta_s)
+    x, info = mp.solve_without_pc(n, A, b_vec, u_vec, verbose=False)
+    ops = O.Operators(n, xi, eta_n, eta_s, c, d)
+    xo, info_o = O.fgmres(ops.A, b_vec, M=None, x0=np.zeros(5 * n * n), tol=1e-8, maxiter=100)
+    assert info != 0 and info_o != 0
+    h, ho = mp.fgmres.last_history, O.fgmres.last_history
+    assert len(h) == len(ho) == 100
+    assert np.allclose(h, ho, rtol=1e-8)
+
+
+def test_known_answer_operator_checks(mp):
+    """utils.check_individual_operators (utils.py:42-157) re-run on the GPU blocks: L1/L2 truncation
+    errors of D, G, XI, L for n = 8, 16, 32 vs the values printed by the reference."""
+    kat = golden("known_answers.npz")
+    PI = np.pi
+    for n in (8, 16, 32):
+        h = 1 / n
+        bp = mp.MultiphaseBlockPreconditioner(n, 1.0, 1.0, 1.0)
+        L, D, XI, G = bp.get_block_matrices(is_ths=False)
+        r = np.arange(n)[:, None] + np.zeros((1, n))
+        c = np.arange(n)[None, :] + np.zeros((n, 1))
+        yu, xu, yv, xv, yp, xp = -(r + .5) * h, c * h, -r * h, (c + .5) * h, -(r + .5) * h, (c + .5) * h
+        ux = lambda y, x: np.sin(2 * PI * x) * np.cos(2 * PI * y)
+        uy = lambda y, x: np.cos(2 * PI * x) * np.sin(2 * PI * y)
+        u = np.concatenate([ux(yu, xu).ravel(), uy(yv, xv).ravel()])
+        pvec = ux(yp, xp).ravel()
+        thn, ths = mp.thn, mp.ths
+        w = h * h
+        exact_D = (2 * PI * np.cos(2 * PI * xp) * np.cos(2 * PI * yp) + 0.5 * PI * np.sin(4 * PI * xp) * np.sin(4 * PI * yp)).ravel()
+        gx = lambda y, x: PI / 2 * np.sin(2*PI*x) * np.sin(2*PI*y) * np.cos(2*PI*x) * np.cos(2*PI*y) + PI * np.cos(2*PI*x) * np.cos(2*PI*y)
+        gy = lambda y, x: -PI / 2 * np.sin(2*PI*x)**2 * np.sin(2*PI*y)**2 - PI * np.sin(2*PI*x) * np.sin(2*PI*y)
+        exact_G = np.concatenate([gx(yu, xu).ravel(), gy(yv, xv).ravel()])
+        exact_XI = np.concatenate([(thn(yu, xu) * ths(yu, xu) * ux(yu, xu)).ravel(), (thn(yv, xv) * ths(yv, xv) * uy(yv, xv)).ravel()])
+        lx = lambda y, x: -4*PI*PI*np.sin(2*PI*x)**2*np.sin(2*PI*y)*np.cos(2*PI*y) - 4*PI*PI*np.sin(2*PI*x)*np.cos(2*PI*y)
+        ly = lambda y, x: -4*PI*PI*np.sin(2*PI*x)*np.cos(2*PI*x)*np.sin(2*PI*y)**2 - 4*PI*PI*np.cos(2*PI*x)*np.sin(2*PI*y)
+        exact_L = np.concatenate([lx(yu, xu).ravel(), ly(yv, xv).ravel()])
+        got = []
+        for ex, ap in ((exact_D, D @ u), (exact_G, G @ pvec), (exact_XI, XI @ u), (exact_L, L @ u)):
+            got += [mp.weighted_L1(ex, ap, w), mp.weighted_L2(ex, ap, w)]
+        assert np.allclose(got, kat[f"opcheck_n{n}"], rtol=1e-7), (n, got, kat[f"opcheck_n{n}"])
+
+
+def test_apply_check_known_answers(mp):
+    """apply.py logic (A u_exact vs b_exact; apply.py:71-81): second-order errors vs the reference's values."""
+    from mp_block_preconditioners_b200.apply import apply_check
+    kat = golden("known_answers.npz")
+    for n in (8, 16, 32):
+        for eta_n in (1.0, 100.0):
+            got = apply_check(n=n, xi=1.0, eta_n=eta_n, eta_s=1.0, c=1.0, d=-1.0, verbose=False)
+            assert np.allclose(got, kat[f"apply_n{n}_eta{int(eta_n)}"], rtol=1e-9), (n, eta_n, got)
+
+
+def test_blas1_kernels(mp):
+    import ctypes as C
+    import torch
+    bp = mp.MultiphaseBlockPreconditioner(64, 1.0, 1.0, 1.0)
+    p = bp.plan(1.0, -1.0, operators_only=True)
+    lib = p.lib
+    from mp_block_preconditioners_b200._cabi import check
+    for length in (1, 31, 1000, 5 * 64 * 64, 1_000_003):
+        g = torch.Generator(device="cuda").manual_seed(length)
+        x = torch.randn(length, dtype=torch.float64, device="cuda", generator=g)
+        y = torch.randn(length, dtype=torch.float64, device="cuda", generator=g)
+        V = torch.randn(11, length, dtype=torch.float64, device="cuda", generator=g)
+        r = C.c_double()
+        check(lib.mpbp_dot(p.h, x.data_ptr(), y.data_ptr(), length, C.byref(r), p.stream()))
+        ref = float((x.cpu().numpy() * y.cpu().numpy()).sum())
+        assert abs(r.value - ref) <= 1e-12 * float((x.abs() * y.abs()).sum())
+        check(lib.mpbp_nrm2(p.h, x.data_ptr(), length, C.byref(r), p.stream()))
+        assert abs(r.value - float(torch.linalg.norm(x))) <= 1e-13 * r.value
+        out = (C.c_double * 11)()
+        check(lib.mpbp_multi_dot(p.h, V.data_ptr(), length, 11, x.data_ptr(), length, out, p.stream()))
+        refm = (V @ x).cpu().numpy()
+        assert np.allclose(np.array(out[:]), refm, rtol=0, atol=1e-12 * float((V.abs() @ x.abs()).max()))
+        al = np.linspace(-1, 1, 11)
+        y2 = y.clone()
+        check(lib.mpbp_multi_axpy(p.h, V.data_ptr(), length, 11, al.ctypes.data_as(C.POINTER(C.c_double)),
+                                  y2.data_ptr(), length, p.stream()))
+        refy = y + torch.from_numpy(al).cuda() @ V
+        assert float((y2 - refy).abs().max()) <= 1e-13 * float(refy.abs().max() + 1)
+        y3 = y.clone()
+        check(lib.mpbp_axpy(p.h, 0.37, x.data_ptr(), y3.data_ptr(), length, p.stream()))
+        assert float((y3 - (y + 0.37 * x)).abs().max()) <= 1e-15 * float(y.abs().max() + 1)
+        out3 = (C.c_double * 3)()
+        check(lib.mpbp_wnorms(p.h, x.data_ptr(), y.data_ptr(), length, 0.25, out3, p.stream()))
+        q = (x - y).abs()
+        assert np.allclose(out3[:], [0.25 * float(q.sum()), float(torch.sqrt(0.25 * (q * q).sum())), float(q.max())], rtol=1e-12)
+    # determinism: identical bits run to run
+    x = torch.randn(5 * 64 * 64, dtype=torch.float64, device="cuda")
+    vals = set()
+    for _ in range(5):
+        r = C.c_double()
+        check(lib.mpbp_dot(p.h, x.data_ptr(), x.data_ptr(), x.numel(), C.byref(r), p.stream()))
+        vals.add(r.value)
+    assert len(vals) == 1
+
+
+def test_error_behaviour(mp):
+    from mp_block_preconditioners_b200._cabi import MpbpError
+    bp = mp.MultiphaseBlockPreconditioner(16, 1.0, 1.0, 1.0)
+    A = bp.get_big_A_matrix(1.0, -1.0)[0]
+    with pytest.raises(ValueError):
+        A @ np.zeros(7)  # dimension mismatch, as np.matmul would raise
+    with pytest.raises(MpbpError):
+        mp.MultiphaseBlockPreconditioner(1, 1.0, 1.0, 1.0).get_big_A_matrix(1.0, -1.0)
+    with pytest.raises(MpbpError):
+        mp.MultiphaseBlockPreconditioner(4094, 1.0, 1.0, 1.0).get_big_A_matrix(1.0, -1.0)  # cannot coarsen
+    p = bp.plan(1.0, -1.0, operators_only=True)
+    with pytest.raises(MpbpError):
+        p.call("mpbp_solve_F", np.zeros(4 * 256), 4 * 256, 4 * 256)
+    with pytest.raises(TypeError):
+        mp.fgmres(np.eye(3), np.zeros(3))
+
+
+@pytest.mark.parametrize("n", [2048, 4096])
+def test_full_size_properties(mp, n):
+    """Size-independent properties at BASELINE.json's grid sizes (the oracle cannot run there):
+    symmetry of A, G^T = -D, linearity, F positive, GtG 1 = 0, sum(D w) = 0, M linear."""
+    import torch
+    eta_n = 1e3 if n == 2048 else 1e4
+    bp = mp.MultiphaseBlockPreconditioner(n, 1.0, eta_n, 1.0, sub_solver=mp.SubSolver(F_cycles=1, P_cycles=1, cheb=False))
+    A, S, F, D, G = bp.get_big_A_matrix(1.0, -1.0)
+    GtG = bp.derived_operators(1.0, -1.0)[0]
+    N = n * n
+    gen = torch.Generator(device="cuda").manual_seed(n)
+    x = torch.randn(5 * N, dtype=torch.float64, device="cuda", generator=gen)
+    y = torch.randn(5 * N, dtype=torch.float64, device="cuda", generator=gen)
+    Ax, Ay = A @ x, A @ y
+    s1, s2 = float(torch.dot(y, Ax)), float(torch.dot(x, Ay))
+    scale = float(torch.linalg.norm(y) * torch.linalg.norm(Ax))
+    assert abs(s1 - s2) < 1e-12 * scale                      # A symmetric (Gt = -D, F symmetric)
+    assert float(torch.linalg.norm(A @ (2.0 * x - 3.0 * y) - (2.0 * Ax - 3.0 * Ay))) < 1e-12 * float(torch.linalg.norm(Ax))
+    w, pr = x[:4 * N], y[4 * N:]
+    Gp, Dw = G @ pr, D @ w
+    assert abs(float(torch.dot(Gp, w)) + float(torch.dot(pr, Dw))) < 1e-12 * float(torch.linalg.norm(Gp) * torch.linalg.norm(w))
+    assert abs(float(Dw.sum())) < 1e-9 * float(Dw.abs().sum())   # discrete divergence theorem
+    assert float(torch.dot(w, F @ w)) > 0                        # F SPD
+    ones = torch.ones(N, dtype=torch.float64, device="cuda")
+    assert float((GtG @ ones).abs().max()) < 1e-6 * n * n        # constants are the null space
+    # block structure: A [w;0] = [F w; -D w]
+    z = torch.cat([w, torch.zeros(N, dtype=torch.float64, device="cuda")])
+    Az = A @ z
+    assert float((Az[:4 * N] - F @ w).abs().max()) <= 1e-13 * float((F @ w).abs().max())
+    assert float((Az[4 * N:] + Dw).abs().max()) <= 1e-13 * float(Dw.abs().max())
+    if n == 2048:
+        M = bp.approx_schur_operator(1.0, -1.0)
+        x2 = x.clone(); y2 = y.clone()
+        x2[4 * N:] -= x2[4 * N:].mean(); y2[4 * N:] -= y2[4 * N:].mean()
+        Mx, My = M @ x2, M @ y2
+        lin = M @ (x2 + 0.5 * y2)
+        assert float(torch.linalg.norm(lin - (Mx + 0.5 * My))) < 1e-9 * float(torch.linalg.norm(Mx))
