@@ -145,12 +145,35 @@ def main():
         out = dict(params=np.array([n, xi, eta_n, eta_s, c, d]), b_vec=b_vec, u_vec=u_vec, v=v, Mv=M.matvec(v),
                    Mb=M.matvec(b_vec), hist=_state["hist"], true_res=np.array(true_res), x=_state["x"],
                    err_norms=np.array(norms))
+        # conditioning of the history itself: re-run with ~1-ulp relative perturbations of b and record
+        # the largest relative change per iteration (the envelope no implementation can beat)
+        def envelope(run, h0):
+            env = np.zeros(len(h0))
+            prng = np.random.default_rng(99)
+            for _ in range(6):
+                bp_ = b_vec * (1.0 + 1.2e-16 * prng.standard_normal(b_vec.shape))
+                h = run(bp_)
+                k = min(len(h), len(h0))
+                env[:k] = np.maximum(env[:k], np.abs(h[:k] - h0[:k]) / h0[:k])
+                if len(h) != len(h0):
+                    env[k:] = np.inf
+            return env
+
+        def run_fg(bb):
+            O.fgmres(A, bb, M=M, tol=1e-8, maxiter=150)
+            return O.fgmres.last_history.copy()
+
+        out["hist_sens"] = envelope(run_fg, _state["hist"])
         # left-preconditioned scipy gmres on the reference's dense A with the same closure
         for restart in (20, 150):
             xs, info, hs = O.gmres_scipy(A, b_vec, M=M, rtol=1e-8, restart=restart, maxiter=40)
             out[f"scipy_hist_r{restart}"] = hs
             out[f"scipy_x_r{restart}"] = xs
             out[f"scipy_info_r{restart}"] = np.array(info)
+            out[f"scipy_sens_r{restart}"] = envelope(
+                lambda bb: O.gmres_scipy(A, bb, M=M, rtol=1e-8, restart=restart, maxiter=40)[2], hs)
+        print("  sens fgmres max", out["hist_sens"].max(), "scipy r20", out["scipy_sens_r20"].max(), "r150",
+              out["scipy_sens_r150"].max())
         np.savez_compressed(os.path.join(HERE, f"solve_{tag}_n{n}_eta{int(eta_n)}.npz"), **out)
         print("solve", tag, n, eta_n, "fgmres its", len(_state["hist"]), "scipy its", len(out["scipy_hist_r20"]),
               len(out["scipy_hist_r150"]), "err norms", norms)
