@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- GMRES iterations/s of the block-preconditioned two-phase Stokes solve (BASELINE.json
+metric) with the roofline of the dominant kernel and the CPU oracle timed beside it.
+
+    python bench.py --gpus N --steps K --warmup W          (N>1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference ...                    (CPU arm: the oracle port on the host cores)
+
+A "step" is one inner iteration of right-preconditioned FGMRES (solve.py:285): one preconditioner apply
+(approx_schur_op, solve.py:257-277), one A.x, and the Arnoldi orthogonalisation at that basis size
+(restart 20).  Workload: 2D 4096^2 MAC grid, 10^4 viscosity contrast (BASELINE.json configs[3]).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(n=4096, eta_n=1.0e4, eta_s=1.0, xi=1.0, c=1.0, d_u=-1.0, restart=20)
+SUB = dict(kind="mg", F_cycles=4, P_cycles=2, cheb=True, nu1=2, nu2=2, omega=0.8, n_coarse=4)
+METRIC = "gmres_iterations_per_second"
+UNIT = "its/s"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (numpy/scipy) on a bounded sample of the workload
+# ----------------------------------------------------------------------------------------------
+def cpu_port_its_per_s(steps, warmup, n_sample=512):
+    """Times `steps` FGMRES iterations of the oracle on an n_sample^2 grid (same contrast, same
+    sub-solver definition, restart 20) and scales its/s to the 4096^2 workload by the cell ratio."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import mpbp_oracle as O
+    w = WORKLOAD
+    ops = O.Operators(n_sample, w["xi"], w["eta_n"], w["eta_s"], w["c"], w["d_u"])
+    cfgF = O.SubSolverConfig(kind="mg", cycles=SUB["F_cycles"], cheb=True)
+    cfgP = O.SubSolverConfig(kind="mg", cycles=SUB["P_cycles"], cheb=True)
+    M = O.ApproxSchur(ops, cfgF)
+    M.P_inv = O.SubSolver(ops, "P", cfgP, O.Multigrid(ops, cfgP))
+    _, b = O.manufactured(n_sample, w["c"], w["d_u"], w["xi"], w["eta_n"], w["eta_s"])
+    Mop = M.linear_operator()
+    if warmup > 0:
+        O.fgmres(ops.A, b, M=Mop, tol=0.0, maxiter=min(warmup, 2), restart=w["restart"])
+    t0 = time.perf_counter()
+    O.fgmres(ops.A, b, M=Mop, tol=0.0, maxiter=steps, restart=w["restart"])
+    dt = time.perf_counter() - t0
+    its = len(O.fgmres.last_history)
+    scale = (n_sample / w["n"]) ** 2
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        threads = os.cpu_count() or 1
+    return dict(value=its / dt * scale, unit=UNIT, cores=threads, kind="port",
+                sample=f"{its} FGMRES iterations of the numpy/scipy oracle on a {n_sample}^2 grid "
+                       f"({dt:.1f} s on the host), its/s scaled by the cell ratio {scale:.5f} to 4096^2; "
+                       f"host has {os.cpu_count()} cores, scipy CSR mat-vec is single-threaded",
+                ms_per_step=dt / its / scale * 1e3)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = min(args.steps, 12)
+    res = cpu_port_its_per_s(steps, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args.gpus), "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def config_dict(ngpu):
+    w = WORKLOAD
+    return {"workload": f"2D {w['n']}^2 MAC grid, viscosity contrast eta_n/eta_s = 1e4, right-preconditioned FGMRES "
+                        f"(restart {w['restart']}), BFBt block preconditioner with Chebyshev-accelerated V(2,2) "
+                        f"multigrid sub-solves (F: {SUB['F_cycles']} cycles, GtG: {SUB['P_cycles']} cycles)",
+            "n": w["n"], "unknowns": 5 * w["n"] ** 2, "eta_n": w["eta_n"], "eta_s": w["eta_s"], "restart": w["restart"],
+            "sub_solver": SUB, "parallelism": f"row-slabs x{ngpu}" if ngpu > 1 else "single GPU",
+            "l2_policy": "inputs_exceed_l2 (one 5N vector = 671 MB vs 126 MB L2)"}
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import ctypes as C
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import mp_block_preconditioners_b200 as mp
+    from mp_block_preconditioners_b200._cabi import SIDE_RIGHT, check
+    from mp_block_preconditioners_b200.solve import _krylov
+    from mp_block_preconditioners_b200.utils import manufactured_device
+
+    w = dict(WORKLOAD)
+    if args.n:
+        w["n"] = args.n
+    n = w["n"]
+    sub = mp.SubSolver(**SUB)
+    bp = mp.MultiphaseBlockPreconditioner(n, w["xi"], w["eta_n"], w["eta_s"], sub_solver=sub, distributed=world > 1)
+    A, S, F, D, G = bp.get_big_A_matrix(c=w["c"], d_u=w["d_u"])
+    M = bp.approx_schur_operator(c=w["c"], d_u=w["d_u"])
+    p = A.plan
+    lib = p.lib
+    N = p.N
+    u_dev, b_dev = manufactured_device(p)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn):
+        """device time of fn() in ms: CUDA events on the launching stream, max over ranks"""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    restart = w["restart"]
+
+    def solve_steps(k):
+        return _krylov(A, b_dev, M, None, 1e-8, restart, 10 ** 6, SIDE_RIGHT, force_iters=k)
+
+    # ---- warm-up (>= 3 iterations) then the timed region ----
+    solve_steps(max(3, args.warmup))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = p.launches
+    ms_total = timed(lambda: solve_steps(args.steps))
+    launches = p.launches - l0
+    value = args.steps / (ms_total * 1e-3)
+
+    # ---- dominant kernel: damped-Jacobi sweep on F at level 0 (k_stokes<2,false>), 104 N algorithmic bytes ----
+    peak, peak_src = measured_peak()
+    xF = torch.zeros(4 * N, dtype=torch.float64, device="cuda")
+    bF = b_dev[:4 * N].contiguous()
+    sweeps = 20
+
+    def jac():
+        check(lib.mpbp_jacobi_F(p.h, bF.data_ptr(), xF.data_ptr(), sweeps, 0.8, p.stream()))
+    jac()
+    ms_jac = timed(jac) / sweeps
+    jac_bytes = 104.0 * N
+    roof = {"bound": "hbm", "kernel": "k_stokes<2,false> (damped-Jacobi sweep on F, level 0)",
+            "achieved": jac_bytes / (ms_jac * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+            "bytes_per_launch": jac_bytes, "ms_per_launch": ms_jac, "traffic": None}
+    roof["frac"] = roof["achieved"] / peak
+
+    # ---- the preconditioner apply as a whole and the other hot kernels ----
+    z = torch.empty_like(b_dev)
+
+    def pc():
+        check(lib.mpbp_precond_apply(p.h, b_dev.data_ptr(), z.data_ptr(), p.stream()))
+    pc()
+    reps = 3
+    ms_pc = timed(lambda: [pc() for _ in range(reps)]) / reps
+    pc_bytes = p.precond_bytes()
+
+    def ax():
+        check(lib.mpbp_apply_A(p.h, b_dev.data_ptr(), z.data_ptr(), p.stream()))
+    ax()
+    ms_ax = timed(lambda: [ax() for _ in range(10)]) / 10
+    kernels = {
+        "precond_apply": {"ms": ms_pc, "algorithmic_bytes": pc_bytes, "gbs": pc_bytes / ms_pc / 1e6,
+                          "frac": pc_bytes / ms_pc / 1e6 / peak},
+        "apply_A": {"ms": ms_ax, "algorithmic_bytes": 88.0 * N, "gbs": 88.0 * N / ms_ax / 1e6,
+                    "frac": 88.0 * N / ms_ax / 1e6 / peak},
+    }
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the public Python API with HOST buffers: one FGMRES cycle per call ----
+    del xF, z
+    e2e_calls = max(1, min(2, args.steps // restart))
+    bh = torch.empty(5 * N, dtype=torch.float64, pin_memory=True)
+    bh.copy_(b_dev)
+    b_host = bh.numpy()
+
+    def e2e_once():
+        x, info = mp.fgmres(A, b_host, M=M, tol=0.0, restart=restart, maxiter=1, host=True)
+        return x
+    e2e_once()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_calls):
+        xh = e2e_once()
+    barrier()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e = {"value": e2e_calls * restart / dt, "unit": UNIT,
+           "h2d_bytes_per_step": 5 * N * 8 * world / restart, "d2h_bytes_per_step": 5 * N * 8 * world / restart,
+           "note": f"host-to-host fgmres(A, b, M=...) calls of one {restart}-iteration cycle each: b copied H2D and x "
+                   f"copied D2H inside every call ({5 * N * 8 * world} bytes each way per call)"}
+
+    if rank == 0:
+        cpu = cpu_port_its_per_s(6, 1) if (world == 1 and not args.no_cpu) else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_dict(world) if not args.n else {**config_dict(world), "n": n, "workload": f"override n={n}"},
+                "roofline": roof, "kernels": kernels, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
+        if cpu:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=0, help="override the grid size (debugging only)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
