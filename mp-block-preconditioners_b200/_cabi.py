@@ -37,6 +37,7 @@ class Config(C.Structure):
         ("lmin", C.c_double), ("lmax", C.c_double),
         ("project", C.c_int),
         ("operators_only", C.c_int),
+        ("dist_min_n", C.c_int),
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_size_t),
     ]

@@ -109,7 +109,23 @@ struct mpbp_plan {
   double* hostbuf_dev[2] = {nullptr, nullptr};  // staging for the *_host entry points
   long long launches = 0;
   cudaStream_t st = nullptr;
+  // ---- peer-memory halo exchange (nranks > 1): ring neighbours push rows into this rank's comm buffer ----
+  bool p2p = false;
+  char* comm_local = nullptr;               // cudaMalloc'd, exported with cudaIpc
+  char *comm_prev = nullptr, *comm_next = nullptr;  // neighbours' comm buffers mapped into this process
+  size_t comm_area = 0;                     // doubles per (slot, direction) halo area
+  unsigned long long seq = 0;               // exchanges issued so far (identical on all ranks)
 };
+
+// comm buffer layout: 4 flags (slot x {top,bot}), 128 B apart, then [slot][dir][5 fields][n0] doubles
+static constexpr size_t kFlagStride = 128;
+static constexpr size_t kFlagBytes = 4 * kFlagStride;
+static inline unsigned long long* comm_flag(char* base, int slot, int dir) {
+  return reinterpret_cast<unsigned long long*>(base + (size_t)(slot * 2 + dir) * kFlagStride);
+}
+static inline double* comm_halo(char* base, size_t area, int slot, int dir) {
+  return reinterpret_cast<double*>(base + kFlagBytes) + (size_t)(slot * 2 + dir) * area;
+}
 
 static constexpr int kScal = 1024;
 
@@ -136,7 +152,8 @@ static int build_levels_shape(const mpbp_config& c, std::vector<Level>& lev, int
       if (rows % 2) return set_err(MPBP_E_ARG, "slab of %d rows at level n=%d cannot be coarsened", rows, n);
       const int nn = n / 2, nrows = rows / 2;
       const bool next_last = (nn <= c.n_coarse) || (nn % 2) || (nn / 2 < 2);
-      if (nrows < 2 || (nrows % 2) || next_last) {
+      const int dmin = c.dist_min_n > 0 ? c.dist_min_n : 1024;
+      if (nrows < 2 || (nrows % 2) || next_last || nn < dmin) {
         dist = false;
         first_repl = (int)lev.size();
       }
@@ -222,6 +239,19 @@ static inline int ew_blocks(size_t len) { return (int)std::min<size_t>((len + 25
 static int halo_exchange(mpbp_plan* p, Level& v, const double* x, int nf, size_t fs) {
   const int P = p->nranks, prev = (p->rank + P - 1) % P, next = (p->rank + 1) % P;
   const size_t n = v.n;
+  if (p->p2p) {
+    // push my boundary rows straight into the neighbours' halo areas (dir 0 = top, 1 = bot) and release
+    // their flags; consumers wait on the flags inside the stencil kernel (edge strips only)
+    const unsigned long long seq = ++p->seq;
+    const int slot = (int)(seq & 1);
+    k_halo_push<<<(nf * v.n + 255) / 256, 256, 0, p->st>>>(
+        x, nf, fs, v.rows, v.n, comm_halo(p->comm_prev, p->comm_area, slot, 1),
+        comm_halo(p->comm_next, p->comm_area, slot, 0), comm_flag(p->comm_prev, slot, 1),
+        comm_flag(p->comm_next, slot, 0), seq, p->counter + 32);
+    p->launches++;
+    CU(cudaGetLastError());
+    return 0;
+  }
   double* top = v.halo;
   double* bot = v.halo + 5 * n;
   NC(ncclGroupStart());
@@ -243,8 +273,17 @@ static int make_view(mpbp_plan* p, Level& v, const double* x, int nf, VecIn& out
   out.fs = fs;
   if (v.dist) {
     RET(halo_exchange(p, v, x, nf, fs));
-    out.top = v.halo;
-    out.bot = v.halo + 5 * (size_t)v.n;
+    if (p->p2p) {
+      const int slot = (int)(p->seq & 1);
+      out.top = comm_halo(p->comm_local, p->comm_area, slot, 0);
+      out.bot = comm_halo(p->comm_local, p->comm_area, slot, 1);
+      out.flag_top = comm_flag(p->comm_local, slot, 0);
+      out.flag_bot = comm_flag(p->comm_local, slot, 1);
+      out.seq = p->seq;
+    } else {
+      out.top = v.halo;
+      out.bot = v.halo + 5 * (size_t)v.n;
+    }
     out.hs = v.n;
   } else {
     out.top = x + (size_t)(v.rows - 1) * v.n;
@@ -263,7 +302,7 @@ static int allreduce_scal(mpbp_plan* p, double* dev, int count) {
 static int op_stokes(mpbp_plan* p, int l, int mode, bool with_p, const double* x, const double* b, double* y,
                      double omega) {
   Level& v = p->lev[l];
-  VecIn in;
+  VecIn in{};
   RET(make_view(p, v, x, with_p ? 5 : 4, in));
   const dim3 grid = stencil_grid(v), block(kBlockThreads);
   if (with_p)
@@ -300,7 +339,7 @@ static int op_poisson(mpbp_plan* p, int l, int mode, const double* x, const doub
 // r = scale * D w + add
 static int op_div(mpbp_plan* p, int l, const double* w, const double* add, double* r, double scale) {
   Level& v = p->lev[l];
-  VecIn in;
+  VecIn in{};
   RET(make_view(p, v, w, 4, in));
   Phys ph = v.ph;
   ph.inv_h *= scale;
@@ -310,7 +349,7 @@ static int op_div(mpbp_plan* p, int l, const double* w, const double* add, doubl
 }
 static int op_grad(mpbp_plan* p, int l, const double* pr, double* y) {
   Level& v = p->lev[l];
-  VecIn in;
+  VecIn in{};
   RET(make_view(p, v, pr, 1, in));
   k_grad<<<stencil_grid(v), kBlockThreads, 0, p->st>>>(in, v.th, y, v.fs(), v.geo, v.ph);
   LAUNCH_CHECK(p);
@@ -331,7 +370,7 @@ static int op_restrict(mpbp_plan* p, int l, bool isF, const double* r) {
   const int rows_c = f.rows / 2, nc = f.n / 2;
   const dim3 block(128), grid((nc + 127) / 128, rows_c);
   if (isF) {
-    VecIn in;
+    VecIn in{};
     RET(make_view(p, f, r, 4, in));
     double* dst = gather ? c.gF : c.bF;
     k_restrict_F<<<grid, block, 0, p->st>>>(in, dst, f.n, f.rows);
@@ -357,7 +396,7 @@ static int op_prolong_add(mpbp_plan* p, int l, bool isF, double* x) {
   Level& c = p->lev[l + 1];
   const dim3 block(128), grid((f.n + 127) / 128, f.rows);
   if (isF) {
-    VecIn in;
+    VecIn in{};
     if (l + 1 == p->first_repl) {
       // coarse level is replicated: address this rank's rows inside the full coarse grid
       const int R0 = f.row0 / 2, rows_c = f.rows / 2, nc = c.n;
@@ -720,6 +759,44 @@ static int build_coarse_inverses(mpbp_plan* p) {
   return 0;
 }
 
+// Peer-memory halo exchange setup: every rank cudaMallocs a small comm buffer, the cudaIpc handles are
+// all-gathered with NCCL and the two ring neighbours' buffers are mapped into this process.
+static int setup_p2p(mpbp_plan* p) {
+  const int P = p->nranks, prev = (p->rank + P - 1) % P, next = (p->rank + 1) % P;
+  p->comm_area = (size_t)5 * p->lev[0].n;
+  const size_t bytes = kFlagBytes + 4 * p->comm_area * sizeof(double);
+  CU(cudaMalloc(&p->comm_local, bytes));
+  CU(cudaMemset(p->comm_local, 0, bytes));
+  cudaIpcMemHandle_t mine;
+  CU(cudaIpcGetMemHandle(&mine, p->comm_local));
+  char* dh = nullptr;
+  CU(cudaMalloc(&dh, (size_t)(P + 1) * sizeof(mine)));
+  CU(cudaMemcpy(dh + (size_t)P * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice));
+  NC(ncclAllGather(dh + (size_t)P * sizeof(mine), dh, sizeof(mine), ncclChar, p->comm, nullptr));
+  CU(cudaStreamSynchronize(nullptr));
+  std::vector<cudaIpcMemHandle_t> all(P);
+  CU(cudaMemcpy(all.data(), dh, (size_t)P * sizeof(mine), cudaMemcpyDeviceToHost));
+  CU(cudaFree(dh));
+  void* pp = nullptr;
+  CU(cudaIpcOpenMemHandle(&pp, all[prev], cudaIpcMemLazyEnablePeerAccess));
+  p->comm_prev = (char*)pp;
+  if (next == prev) {
+    p->comm_next = p->comm_prev;
+  } else {
+    CU(cudaIpcOpenMemHandle(&pp, all[next], cudaIpcMemLazyEnablePeerAccess));
+    p->comm_next = (char*)pp;
+  }
+  // nobody may push before every rank has zeroed and mapped its buffers
+  double* tok = nullptr;
+  CU(cudaMalloc(&tok, sizeof(double)));
+  CU(cudaMemset(tok, 0, sizeof(double)));
+  NC(ncclAllReduce(tok, tok, 1, ncclDouble, ncclSum, p->comm, nullptr));
+  CU(cudaStreamSynchronize(nullptr));
+  CU(cudaFree(tok));
+  p->p2p = true;
+  return 0;
+}
+
 extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
   if (!out) return set_err(MPBP_E_ARG, "null plan pointer");
   *out = nullptr;
@@ -772,6 +849,11 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
     memcpy(&id, cfg->nccl_unique_id, sizeof(id));
     ncclResult_t e = ncclCommInitRank(&p->comm, p->nranks, id, p->rank);
     if (e != ncclSuccess) return fail(set_err(1000 + (int)e, "ncclCommInitRank: %s", ncclGetErrorString(e)));
+    const char* mode = getenv("MPBP_HALO");
+    if (!(mode && strcmp(mode, "nccl") == 0)) {
+      rc = setup_p2p(p);
+      if (rc) return fail(rc);
+    }
   }
 
   // ---- coefficient fields on the host: theta_n per level (4-cell averages), mass-term tables ----
@@ -847,6 +929,10 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   p->red_blocks = std::min(kMaxRedBlocks, sms * 4);
+  if (const char* rb = getenv("MPBP_RED_BLOCKS")) {  // testing knob: changes the (deterministic) summation order
+    const int v = atoi(rb);
+    if (v >= 1 && v <= kMaxRedBlocks) p->red_blocks = v;
+  }
   if (!cfg->operators_only) {
     rc = build_coarse_inverses(p);
     if (rc) return fail(rc);
@@ -860,7 +946,11 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
 extern "C" int mpbp_plan_destroy(mpbp_plan* p) {
   if (!p) return 0;
   cudaDeviceSynchronize();
+  if (p->comm_prev) cudaIpcCloseMemHandle(p->comm_prev);
+  if (p->comm_next && p->comm_next != p->comm_prev) cudaIpcCloseMemHandle(p->comm_next);
+  // (destroy is not collective: callers finish all solves on every rank before dropping their plans)
   if (p->comm) ncclCommDestroy(p->comm);
+  if (p->comm_local) cudaFree(p->comm_local);
   if (p->owned) cudaFree(p->owned);
   if (p->kry_owned) cudaFree(p->kry_owned);
   for (int i = 0; i < 2; ++i)

@@ -40,7 +40,63 @@ struct VecIn {
   const double* top;
   const double* bot;
   size_t fs, hs;
+  // multi-GPU: the halo rows are pushed into this rank's memory by the ring neighbours (peer stores over
+  // NVLink); blocks that read them first wait until the neighbour's flag reaches `seq` (null: no wait)
+  const unsigned long long* flag_top;
+  const unsigned long long* flag_bot;
+  unsigned long long seq;
 };
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// warp-level wait for the neighbours' halo rows (called by whole warps; lane 0 polls)
+__device__ __forceinline__ void halo_wait(const VecIn& v, bool need_top, bool need_bot) {
+  if (v.flag_top == nullptr) return;
+  if ((threadIdx.x & 31) == 0) {
+    if (need_top)
+      while (ld_acquire_sys(v.flag_top) < v.seq) {
+      }
+    if (need_bot)
+      while (ld_acquire_sys(v.flag_bot) < v.seq) {
+      }
+  }
+  __syncwarp();
+}
+
+// Halo push: copies this rank's first / last slab row of every field into the ring neighbours' halo
+// buffers (peer memory over NVLink) and then releases their flags.  One thread per (field, column);
+// the last block to finish publishes the flags.  Replaces an ncclSend/ncclRecv pair per field and
+// direction.
+__global__ void __launch_bounds__(256) k_halo_push(const double* __restrict__ x, int nf, size_t fs, int rows, int n,
+                                                   double* __restrict__ prev_bot, double* __restrict__ next_top,
+                                                   unsigned long long* prev_flag_bot, unsigned long long* next_flag_top,
+                                                   unsigned long long seq, unsigned int* done_counter) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nf * n) {
+    const int k = i / n, c = i - k * n;
+    const double first = x[k * fs + c];
+    const double last = x[k * fs + (size_t)(rows - 1) * n + c];
+    prev_bot[i] = first;  // my first row is the previous rank's row `rows`
+    next_top[i] = last;   // my last row is the next rank's row -1
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(done_counter, 1u);
+    if (t == gridDim.x - 1) {
+      *done_counter = 0u;
+      __threadfence_system();
+      st_release_sys(prev_flag_bot, seq);
+      st_release_sys(next_flag_top, seq);
+    }
+  }
+}
 
 struct Geo {
   int n;     // columns (= global grid size of the level)
@@ -108,6 +164,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_stokes(VecIn xin, const doubl
   const int r0 = blockIdx.y * g.rs;
   const int r1 = min(r0 + g.rs, rows);
   if (r0 >= rows) return;
+  halo_wait(xin, r0 == 0, r1 == rows);
 
   double sxf = 0.0, sxc = 0.0;
   if (ph.mass_mode) {
@@ -311,6 +368,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_poisson(VecIn pin, const doub
   const int r0 = blockIdx.y * g.rs;
   const int r1 = min(r0 + g.rs, rows);
   if (r0 >= rows) return;
+  if (MODE != 3) halo_wait(pin, r0 == 0, r1 == rows);
   double th_m = th_row(th, r0 - 1, n)[c];
   double th_c = th_row(th, r0, n)[c];
   double p_m = 0.0, p_c = 0.0;
@@ -356,6 +414,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_div(VecIn win, const double* 
   const int r0 = blockIdx.y * g.rs;
   const int r1 = min(r0 + g.rs, rows);
   if (r0 >= rows) return;
+  halo_wait(win, false, r1 == rows);
   double th_m = th_row(th, r0 - 1, n)[c];
   double th_c = th_row(th, r0, n)[c];
   double vn_c = row_ptr(win, 1, r0, rows, n)[c], vs_c = row_ptr(win, 3, r0, rows, n)[c];
@@ -387,6 +446,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_grad(VecIn pin, const double*
   const int r0 = blockIdx.y * g.rs;
   const int r1 = min(r0 + g.rs, rows);
   if (r0 >= rows) return;
+  halo_wait(pin, r0 == 0, false);
   double th_m = th_row(th, r0 - 1, n)[c];
   double p_m = row_ptr(pin, 0, r0 - 1, rows, n)[c];
 #pragma unroll 2
@@ -416,6 +476,7 @@ __global__ void k_restrict_F(VecIn fin, double* __restrict__ yc, int nf, int row
   const int nc = nf >> 1, rows_c = rows_f >> 1;
   const int C = blockIdx.x * blockDim.x + threadIdx.x;
   const int R = blockIdx.y;
+  halo_wait(fin, R == 0, false);
   if (C >= nc || R >= rows_c) return;
   const size_t fsc = (size_t)rows_c * nc;
   const int c0 = 2 * C, cm = (c0 == 0) ? nf - 1 : c0 - 1, cp = c0 + 1;
@@ -439,6 +500,7 @@ __global__ void k_prolong_add_F(VecIn cin, double* __restrict__ xf, int nf, int 
   const int nc = nf >> 1, rows_c = rows_f >> 1;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;
+  halo_wait(cin, false, r == rows_f - 1);
   if (c >= nf || r >= rows_f) return;
   const size_t fsf = (size_t)rows_f * nf;
   const int C = c >> 1, R = r >> 1;

@@ -49,6 +49,7 @@ class SubSolver:
     lmin: float = 0.75
     lmax: float = 1.2
     project: bool = True
+    dist_min_n: int = 0  # multi-GPU: levels with n < dist_min_n are replicated (0 = library default 1024)
 
 
 def _stream_ptr(device):
@@ -78,6 +79,7 @@ class Plan:
         cfg.omega, cfg.nu1, cfg.nu2, cfg.n_coarse = sub.omega, sub.nu1, sub.nu2, sub.n_coarse
         cfg.cheb, cfg.lmin, cfg.lmax, cfg.project = int(sub.cheb), sub.lmin, sub.lmax, int(sub.project)
         cfg.operators_only = int(operators_only)
+        cfg.dist_min_n = int(sub.dist_min_n)
         self._keep = []
         if theta is not None:
             th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64).reshape(n, n))

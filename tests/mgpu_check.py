@@ -26,7 +26,8 @@ def main():
 
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     xi, eta_n, eta_s, c, d = 1.0, 100.0, 1.0, 1.0, -1.0
-    sub = mp.SubSolver(kind="mg", F_cycles=3, P_cycles=2, cheb=True)
+    dmin = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    sub = mp.SubSolver(kind="mg", F_cycles=3, P_cycles=2, cheb=True, dist_min_n=dmin)
     ok = True
 
     def report(name, err, tol):
@@ -77,13 +78,42 @@ def main():
     u1, b1 = manufactured_device(A1.plan)
     ud, bd = manufactured_device(p)
     report("manufactured_rhs", rel(bd, scatter_slab(b1, n, 5, rank, world)), 1e-15)
-    for side, name in ((SIDE_RIGHT, "fgmres"), (SIDE_LEFT, "gmres_left")):
-        xa, ia, ha = _krylov(A1, b1, M1, None, 1e-8, 30, 40 if side == SIDE_RIGHT else 5, side)
-        xb, ib, hb = _krylov(Ad, bd, Md, None, 1e-8, 30, 40 if side == SIDE_RIGHT else 5, side)
-        k = min(len(ha), len(hb))
-        report(f"{name}_iterations(|d|<=1) {len(ha)}/{len(hb)}", float(abs(len(ha) - len(hb))), 1.5)
-        report(f"{name}_history", float(np.abs(ha[:k] - hb[:k]).max() / ha[0]), 1e-7)
-        report(f"{name}_solution", rel(xb, scatter_slab(xa, n, 5, rank, world)), 1e-5)
+    def krylov_pair(tag, eta, A1_, M1_, Ad_, Md_, b1_, bd_, sides):
+        # conditioning of the history: the same single-GPU solve with a different (still deterministic)
+        # summation order in the dot products -- the only arithmetic difference a slab run introduces
+        os.environ["MPBP_RED_BLOCKS"] = "211"
+        bps = mp.MultiphaseBlockPreconditioner(n, xi, eta, eta_s, sub_solver=sub)
+        As, Ms = bps.get_big_A_matrix(c, d)[0], bps.approx_schur_operator(c, d)
+        del os.environ["MPBP_RED_BLOCKS"]
+        for side, name in sides:
+            mi = 60 if side == SIDE_RIGHT else 5
+            xa, ia, ha = _krylov(A1_, b1_, M1_, None, 1e-8, 30, mi, side)
+            xb, ib, hb = _krylov(Ad_, bd_, Md_, None, 1e-8, 30, mi, side)
+            xs_, is_, hs_ = _krylov(As, b1_, Ms, None, 1e-8, 30, mi, side)
+            k = min(len(ha), len(hb), len(hs_))
+            sens = np.abs(ha[:k] - hs_[:k]) / ha[:k]
+            allowed = np.maximum(1e-9, 1e3 * sens)
+            dev = np.abs(ha[:k] - hb[:k]) / ha[:k]
+            if rank == 0:
+                print(f"   {tag}{name}: its 1gpu/slab/1gpu' = {len(ha)}/{len(hb)}/{len(hs_)}, max rel dev {dev.max():.2e}, "
+                      f"max 1-GPU reorder sensitivity {sens.max():.2e}, info {ia}/{ib}", flush=True)
+            report(f"{tag}{name}_iterations(|d|<=1+|d_reorder|)", float(abs(len(ha) - len(hb))), 1.5 + abs(len(ha) - len(hs_)))
+            report(f"{tag}{name}_history_vs_conditioning", float((dev / allowed).max()), 1.0)
+            report(f"{tag}{name}_converged_both", float(ia + ib), 0.5)
+            xtol = max(1e-6, 1e3 * rel(xs_, xa))
+            report(f"{tag}{name}_solution", rel(xb, scatter_slab(xa, n, 5, rank, world)), xtol)
+
+    # eta_n = 100: right-preconditioned FGMRES (the left-preconditioned history is ill conditioned at this
+    # contrast -- the oracle itself moves by tens of percent under 1-ulp perturbations, tests/golden)
+    krylov_pair("eta100_", eta_n, A1, M1, Ad, Md, b1, bd, ((SIDE_RIGHT, "fgmres"),))
+    # eta_n = 1: both Krylov variants
+    bp1b = mp.MultiphaseBlockPreconditioner(n, xi, 1.0, eta_s, sub_solver=sub)
+    bpdb = mp.MultiphaseBlockPreconditioner(n, xi, 1.0, eta_s, sub_solver=sub, distributed=True)
+    A1b, Adb = bp1b.get_big_A_matrix(c, d)[0], bpdb.get_big_A_matrix(c, d)[0]
+    M1b, Mdb = bp1b.approx_schur_operator(c, d), bpdb.approx_schur_operator(c, d)
+    _, b1b = manufactured_device(A1b.plan)
+    _, bdb = manufactured_device(Adb.plan)
+    krylov_pair("eta1_", 1.0, A1b, M1b, Adb, Mdb, b1b, bdb, ((SIDE_RIGHT, "fgmres"), (SIDE_LEFT, "gmres_left")))
     if rank == 0:
         print("MGPU_ALL_PASS" if ok else "MGPU_FAILED", flush=True)
     dist.barrier()
