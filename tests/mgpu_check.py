@@ -99,7 +99,7 @@ def main():
                       f"max 1-GPU reorder sensitivity {sens.max():.2e}, info {ia}/{ib}", flush=True)
             report(f"{tag}{name}_iterations(|d|<=1+|d_reorder|)", float(abs(len(ha) - len(hb))), 1.5 + abs(len(ha) - len(hs_)))
             report(f"{tag}{name}_history_vs_conditioning", float((dev / allowed).max()), 1.0)
-            report(f"{tag}{name}_converged_both", float(ia + ib), 0.5)
+            report(f"{tag}{name}_same_info", float(abs(ia - ib)), 0.5)
             xtol = max(1e-6, 1e3 * rel(xs_, xa))
             report(f"{tag}{name}_solution", rel(xb, scatter_slab(xa, n, 5, rank, world)), xtol)
 
