@@ -108,24 +108,22 @@ struct mpbp_plan {
   size_t kry_owned_bytes = 0;
   double* hostbuf_dev[2] = {nullptr, nullptr};  // staging for the *_host entry points
   long long launches = 0;
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr;    // the plan's own stream: all work runs here, fenced against the caller's stream
+  cudaStream_t ust = nullptr;   // caller's stream of the current API call
+  cudaStream_t own = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // V-cycles (rin -> z) replay as CUDA graphs: ~100 small launches per cycle become one graph launch
+  bool use_graph = true;
+  cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+  long long glaunches[2] = {0, 0};
   // ---- peer-memory halo exchange (nranks > 1): ring neighbours push rows into this rank's comm buffer ----
   bool p2p = false;
   char* comm_local = nullptr;               // cudaMalloc'd, exported with cudaIpc
   char *comm_prev = nullptr, *comm_next = nullptr;  // neighbours' comm buffers mapped into this process
   size_t comm_area = 0;                     // doubles per (slot, direction) halo area
-  unsigned long long seq = 0;               // exchanges issued so far (identical on all ranks)
+  unsigned long long* dseq = nullptr;       // device-resident exchange counter (identical on all ranks)
 };
 
-// comm buffer layout: 4 flags (slot x {top,bot}), 128 B apart, then [slot][dir][5 fields][n0] doubles
-static constexpr size_t kFlagStride = 128;
-static constexpr size_t kFlagBytes = 4 * kFlagStride;
-static inline unsigned long long* comm_flag(char* base, int slot, int dir) {
-  return reinterpret_cast<unsigned long long*>(base + (size_t)(slot * 2 + dir) * kFlagStride);
-}
-static inline double* comm_halo(char* base, size_t area, int slot, int dir) {
-  return reinterpret_cast<double*>(base + kFlagBytes) + (size_t)(slot * 2 + dir) * area;
-}
 
 static constexpr int kScal = 1024;
 
@@ -218,6 +216,7 @@ static void carve(mpbp_plan* p, Bump& B) {
   p->partial = B.take<double>((size_t)kMaxRedBlocks * kMaxMulti);
   p->counter = B.take<unsigned int>(64);
   p->scal = B.take<double>(kScal);
+  p->dseq = B.take<unsigned long long>(16);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -242,12 +241,8 @@ static int halo_exchange(mpbp_plan* p, Level& v, const double* x, int nf, size_t
   if (p->p2p) {
     // push my boundary rows straight into the neighbours' halo areas (dir 0 = top, 1 = bot) and release
     // their flags; consumers wait on the flags inside the stencil kernel (edge strips only)
-    const unsigned long long seq = ++p->seq;
-    const int slot = (int)(seq & 1);
-    k_halo_push<<<(nf * v.n + 255) / 256, 256, 0, p->st>>>(
-        x, nf, fs, v.rows, v.n, comm_halo(p->comm_prev, p->comm_area, slot, 1),
-        comm_halo(p->comm_next, p->comm_area, slot, 0), comm_flag(p->comm_prev, slot, 1),
-        comm_flag(p->comm_next, slot, 0), seq, p->counter + 32);
+    k_halo_push<<<(nf * v.n + 255) / 256, 256, 0, p->st>>>(x, nf, fs, v.rows, v.n, p->comm_prev, p->comm_next,
+                                                           p->comm_area, p->dseq, p->counter + 32);
     p->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -274,12 +269,10 @@ static int make_view(mpbp_plan* p, Level& v, const double* x, int nf, VecIn& out
   if (v.dist) {
     RET(halo_exchange(p, v, x, nf, fs));
     if (p->p2p) {
-      const int slot = (int)(p->seq & 1);
-      out.top = comm_halo(p->comm_local, p->comm_area, slot, 0);
-      out.bot = comm_halo(p->comm_local, p->comm_area, slot, 1);
-      out.flag_top = comm_flag(p->comm_local, slot, 0);
-      out.flag_bot = comm_flag(p->comm_local, slot, 1);
-      out.seq = p->seq;
+      out.dseq = p->dseq;
+      out.comm = p->comm_local;
+      out.area = p->comm_area;
+      out.top = out.bot = nullptr;  // resolved on the device from *dseq
     } else {
       out.top = v.halo;
       out.bot = v.halo + 5 * (size_t)v.n;
@@ -548,6 +541,33 @@ static int vcycle(mpbp_plan* p, int l, bool isF, const double* b, double* x) {
   return 0;
 }
 
+// V-cycle on the fixed internal buffers rin -> z, replayed as a CUDA graph after the first capture
+static int vcycle_fixed(mpbp_plan* p, bool isF) {
+  const double* rin = isF ? p->rinF : p->rinP;
+  double* z = isF ? p->zF : p->zP;
+  if (!p->use_graph) return vcycle(p, 0, isF, rin, z);
+  const int idx = isF ? 0 : 1;
+  if (!p->gexec[idx]) {
+    const long long l0 = p->launches;
+    CU(cudaStreamBeginCapture(p->st, cudaStreamCaptureModeThreadLocal));
+    const int rc = vcycle(p, 0, isF, rin, z);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(p->st, &g);
+    if (rc != 0) {
+      if (g) cudaGraphDestroy(g);
+      return rc;
+    }
+    CU(e);
+    CU(cudaGraphInstantiate(&p->gexec[idx], g, 0));
+    cudaGraphDestroy(g);
+    p->glaunches[idx] = p->launches - l0;
+    p->launches = l0;
+  }
+  CU(cudaGraphLaunch(p->gexec[idx], p->st));
+  p->launches += p->glaunches[idx];
+  return 0;
+}
+
 static int project_mean(mpbp_plan* p, double* x) {
   Level& v = p->lev[0];
   const size_t len = v.fs();
@@ -580,12 +600,14 @@ static int sub_solve(mpbp_plan* p, bool isF, const double* b, double* x) {
     double* rin = isF ? p->rinF : p->rinP;
     double* z = isF ? p->zF : p->zP;
     double* dv = isF ? p->dvF : p->dvP;
+    RET(v_copy(p, b, rin, len));  // every cycle runs rin -> z on fixed buffers (graph replay)
     if (!c.cheb) {
-      RET(vcycle(p, 0, isF, b, x));
+      RET(vcycle_fixed(p, isF));
+      RET(v_copy(p, z, x, len));
       for (int k = 1; k < cycles; ++k) {
         if (isF) RET(op_stokes(p, 0, 1, false, x, b, rin, 0.0));
         else RET(op_poisson(p, 0, 1, x, b, rin, 0.0));
-        RET(vcycle(p, 0, isF, rin, z));
+        RET(vcycle_fixed(p, isF));
         RET(v_axpby(p, 1.0, x, 1.0, z, x, len));
       }
     } else {
@@ -593,13 +615,13 @@ static int sub_solve(mpbp_plan* p, bool isF, const double* b, double* x) {
       const double th = 0.5 * (c.lmax + c.lmin), de = 0.5 * (c.lmax - c.lmin);
       const double sig = th / de;
       double rho_k = 1.0 / sig;
-      RET(vcycle(p, 0, isF, b, z));
+      RET(vcycle_fixed(p, isF));
       RET(v_axpby(p, 1.0 / th, z, 0.0, z, dv, len));
       RET(v_copy(p, dv, x, len));
       for (int k = 1; k < cycles; ++k) {
         if (isF) RET(op_stokes(p, 0, 1, false, x, b, rin, 0.0));
         else RET(op_poisson(p, 0, 1, x, b, rin, 0.0));
-        RET(vcycle(p, 0, isF, rin, z));
+        RET(vcycle_fixed(p, isF));
         const double rho_n = 1.0 / (2.0 * sig - rho_k);
         k_cheb_update<<<ew_blocks(len), 256, 0, p->st>>>(rho_n * rho_k, 2.0 * rho_n / de, z, dv, x, len);
         LAUNCH_CHECK(p);
@@ -839,9 +861,15 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
     cudaError_t e = cudaMallocHost(&p->hscal, kScal * sizeof(double));
     if (e != cudaSuccess) { mpbp_plan_destroy(p); return set_err((int)e, "cudaMallocHost failed"); }
   }
-  p->st = nullptr;
   auto fail = [&](int code) { mpbp_plan_destroy(p); return code; };
-  if (cudaMemsetAsync(p->counter, 0, 64 * sizeof(unsigned int), nullptr) != cudaSuccess)
+  if (cudaStreamCreateWithFlags(&p->own, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming) != cudaSuccess)
+    return fail(set_err(999, "stream/event creation failed"));
+  p->st = p->own;
+  if (const char* e = getenv("MPBP_GRAPH")) p->use_graph = atoi(e) != 0;
+  if (cudaMemsetAsync(p->counter, 0, 64 * sizeof(unsigned int), nullptr) != cudaSuccess ||
+      cudaMemsetAsync(p->dseq, 0, 16 * sizeof(unsigned long long), nullptr) != cudaSuccess)
     return fail(set_err(999, "memset failed"));
 
   if (p->nranks > 1) {
@@ -923,6 +951,9 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
       const int gx = (n + kWarpCols * kBlockWarps - 1) / (kWarpCols * kBlockWarps);
       while (rs > 4 && gx * ((v.rows + rs - 1) / rs) < 592) rs /= 2;
       v.geo.rs = std::max(1, std::min(rs, v.rows));
+      v.geo.pf = 3;  // measured best on B200 at 4096^2 (profiles/r1_pf_sweep.txt)
+      if (const char* e = getenv("MPBP_PF")) v.geo.pf = std::max(0, std::min(atoi(e), 64));
+      if (const char* e = getenv("MPBP_RS")) v.geo.rs = std::max(1, std::min(atoi(e), v.rows));
     }
   }
   int dev = 0, sms = 148;
@@ -950,6 +981,11 @@ extern "C" int mpbp_plan_destroy(mpbp_plan* p) {
   if (p->comm_next && p->comm_next != p->comm_prev) cudaIpcCloseMemHandle(p->comm_next);
   // (destroy is not collective: callers finish all solves on every rank before dropping their plans)
   if (p->comm) ncclCommDestroy(p->comm);
+  for (int i = 0; i < 2; ++i)
+    if (p->gexec[i]) cudaGraphExecDestroy(p->gexec[i]);
+  if (p->ev_in) cudaEventDestroy(p->ev_in);
+  if (p->ev_out) cudaEventDestroy(p->ev_out);
+  if (p->own) cudaStreamDestroy(p->own);
   if (p->comm_local) cudaFree(p->comm_local);
   if (p->owned) cudaFree(p->owned);
   if (p->kry_owned) cudaFree(p->kry_owned);
@@ -978,76 +1014,129 @@ extern "C" long long mpbp_plan_launches(const mpbp_plan* p) { return p ? p->laun
 // ---------------------------------------------------------------------------------------------
 // exported operator applies
 // ---------------------------------------------------------------------------------------------
+// every export runs on the plan's own stream between two event fences against the caller's stream
+static int enter(mpbp_plan* p, void* stream) {
+  p->ust = (cudaStream_t)stream;
+  p->st = p->own;
+  CU(cudaEventRecord(p->ev_in, p->ust));
+  CU(cudaStreamWaitEvent(p->own, p->ev_in, 0));
+  return 0;
+}
+static int leave(mpbp_plan* p, int rc) {
+  cudaError_t e = cudaEventRecord(p->ev_out, p->own);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(p->ust, p->ev_out, 0);
+  if (rc == 0 && e != cudaSuccess) return set_err((int)e, "stream fence failed: %s", cudaGetErrorString(e));
+  return rc;
+}
 #define ENTER(p, stream)                               \
   if (!(p)) return set_err(MPBP_E_ARG, "null plan");   \
-  (p)->st = (cudaStream_t)(stream);
+  RET(enter((p), (stream)));
 
 extern "C" int mpbp_apply_A(mpbp_plan* p, const double* x, double* y, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!x || !y || x == y) return set_err(MPBP_E_ARG, "apply_A: bad pointers");
   return op_stokes(p, 0, 0, true, x, nullptr, y, 0.0);
+  };
+  return leave(p, body());
 }
 extern "C" int mpbp_apply_F(mpbp_plan* p, const double* x, double* y, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!x || !y || x == y) return set_err(MPBP_E_ARG, "apply_F: bad pointers");
   return op_stokes(p, 0, 0, false, x, nullptr, y, 0.0);
+  };
+  return leave(p, body());
 }
 extern "C" int mpbp_apply_G(mpbp_plan* p, const double* pr, double* y, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!pr || !y) return set_err(MPBP_E_ARG, "apply_G: bad pointers");
   return op_grad(p, 0, pr, y);
+  };
+  return leave(p, body());
 }
 extern "C" int mpbp_apply_D(mpbp_plan* p, const double* w, const double* add, double* r, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!w || !r) return set_err(MPBP_E_ARG, "apply_D: bad pointers");
   return op_div(p, 0, w, add, r, 1.0);
+  };
+  return leave(p, body());
 }
 extern "C" int mpbp_apply_GtG(mpbp_plan* p, const double* pr, double* y, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!pr || !y || pr == y) return set_err(MPBP_E_ARG, "apply_GtG: bad pointers");
   return op_poisson(p, 0, 0, pr, nullptr, y, 0.0);
+  };
+  return leave(p, body());
 }
 extern "C" int mpbp_apply_GtFG(mpbp_plan* p, const double* pr, double* y, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!pr || !y) return set_err(MPBP_E_ARG, "apply_GtFG: bad pointers");
   RET(op_grad(p, 0, pr, p->g));
   RET(op_stokes(p, 0, 0, false, p->g, nullptr, p->t2, 0.0));
   return op_div(p, 0, p->t2, nullptr, y, -1.0);
+  };
+  return leave(p, body());
 }
 extern "C" int mpbp_jacobi_F(mpbp_plan* p, const double* b, double* x, int sweeps, double omega, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!b || !x || sweeps < 0) return set_err(MPBP_E_ARG, "jacobi_F: bad arguments");
   return jacobi_sweeps(p, 0, true, b, x, p->lev[0].tF, sweeps, omega);
+  };
+  return leave(p, body());
 }
 extern "C" int mpbp_jacobi_P(mpbp_plan* p, const double* b, double* x, int sweeps, double omega, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!b || !x || sweeps < 0) return set_err(MPBP_E_ARG, "jacobi_P: bad arguments");
   return jacobi_sweeps(p, 0, false, b, x, p->lev[0].tP, sweeps, omega);
+  };
+  return leave(p, body());
 }
 extern "C" int mpbp_vcycle_F(mpbp_plan* p, const double* b, double* x, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!b || !x || b == x) return set_err(MPBP_E_ARG, "vcycle_F: bad pointers");
   return vcycle(p, 0, true, b, x);
+  };
+  return leave(p, body());
 }
 extern "C" int mpbp_vcycle_P(mpbp_plan* p, const double* b, double* x, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!b || !x || b == x) return set_err(MPBP_E_ARG, "vcycle_P: bad pointers");
   return vcycle(p, 0, false, b, x);
+  };
+  return leave(p, body());
 }
 extern "C" int mpbp_solve_F(mpbp_plan* p, const double* b, double* x, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!b || !x || b == x) return set_err(MPBP_E_ARG, "solve_F: bad pointers");
   return sub_solve(p, true, b, x);
+  };
+  return leave(p, body());
 }
 extern "C" int mpbp_solve_P(mpbp_plan* p, const double* b, double* x, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!b || !x || b == x) return set_err(MPBP_E_ARG, "solve_P: bad pointers");
   return sub_solve(p, false, b, x);
+  };
+  return leave(p, body());
 }
 extern "C" int mpbp_precond_apply(mpbp_plan* p, const double* v, double* z, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!v || !z || v == z) return set_err(MPBP_E_ARG, "precond_apply: bad pointers");
   return precond_apply(p, v, z);
+  };
+  return leave(p, body());
 }
 
 static int ensure_hostbuf(mpbp_plan* p) {
@@ -1058,6 +1147,7 @@ static int ensure_hostbuf(mpbp_plan* p) {
 }
 extern "C" int mpbp_precond_apply_host(mpbp_plan* p, const double* v_host, double* z_host, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!v_host || !z_host) return set_err(MPBP_E_ARG, "precond_apply_host: bad pointers");
   RET(ensure_hostbuf(p));
   const size_t bytes = 5 * p->lev[0].fs() * sizeof(double);
@@ -1066,6 +1156,8 @@ extern "C" int mpbp_precond_apply_host(mpbp_plan* p, const double* v_host, doubl
   CU(cudaMemcpyAsync(z_host, p->hostbuf_dev[1], bytes, cudaMemcpyDeviceToHost, p->st));
   CU(cudaStreamSynchronize(p->st));
   return 0;
+  };
+  return leave(p, body());
 }
 
 // algorithmic bytes (SURVEY 8d accounting: every input read once, every output written once, one
@@ -1105,7 +1197,8 @@ static double solve_bytes(const mpbp_plan* p, bool isF) {
     by = k * vcycle_bytes(p, 0, isF);
     by += (k - 1) * (isF ? 104 * N : 32 * N);                 // residual before every extra cycle
     by += (k - 1) * (c.cheb ? 5 * vec : 3 * vec);             // x += z  / Chebyshev update
-    if (c.cheb) by += 4 * vec;                                // d = z/theta ; x = d
+    by += 2 * vec;                                            // rin = b (cycles run on fixed buffers)
+    by += c.cheb ? 4 * vec : 2 * vec;                         // d = z/theta ; x = d   /   x = z
   }
   if (!isF && c.project) by += 3 * 8 * N;
   return by;
@@ -1127,43 +1220,59 @@ extern "C" int mpbp_precond_bytes(const mpbp_plan* p, double* bytes) {
 // ---------------------------------------------------------------------------------------------
 extern "C" int mpbp_dot(mpbp_plan* p, const double* x, const double* y, size_t len, double* result, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!x || !y || !result) return set_err(MPBP_E_ARG, "dot: bad pointers");
   RET(v_dot(p, x, y, len, p->scal));
   RET(fetch_scal(p, p->scal, 1, p->hscal));
   *result = p->hscal[0];
   return 0;
+  };
+  return leave(p, body());
 }
 extern "C" int mpbp_nrm2(mpbp_plan* p, const double* x, size_t len, double* result, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!x || !result) return set_err(MPBP_E_ARG, "nrm2: bad pointers");
   RET(v_nrm2(p, x, len, p->scal));
   RET(fetch_scal(p, p->scal, 1, p->hscal));
   *result = p->hscal[0];
   return 0;
+  };
+  return leave(p, body());
 }
 extern "C" int mpbp_axpy(mpbp_plan* p, double alpha, const double* x, double* y, size_t len, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!x || !y) return set_err(MPBP_E_ARG, "axpy: bad pointers");
   return v_multi_axpy(p, x, 0, 1, &alpha, y, len);
+  };
+  return leave(p, body());
 }
 extern "C" int mpbp_multi_dot(mpbp_plan* p, const double* V, size_t ld, int nvec, const double* w, size_t len,
                               double* out, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!V || !w || !out || nvec < 1 || nvec > kScal - 8) return set_err(MPBP_E_ARG, "multi_dot: bad arguments");
   RET(v_multi_dot(p, V, ld, nvec, w, len, p->scal, false));
   RET(fetch_scal(p, p->scal, nvec, p->hscal));
   memcpy(out, p->hscal, nvec * sizeof(double));
   return 0;
+  };
+  return leave(p, body());
 }
 extern "C" int mpbp_multi_axpy(mpbp_plan* p, const double* V, size_t ld, int nvec, const double* alpha, double* w,
                                size_t len, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!V || !w || !alpha || nvec < 1) return set_err(MPBP_E_ARG, "multi_axpy: bad arguments");
   return v_multi_axpy(p, V, ld, nvec, alpha, w, len);
+  };
+  return leave(p, body());
 }
 extern "C" int mpbp_wnorms(mpbp_plan* p, const double* a, const double* b, size_t len, double w, double* out3,
                            void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!a || !b || !out3) return set_err(MPBP_E_ARG, "wnorms: bad pointers");
   const int blocks = (int)std::min<size_t>((len + kRedThreads - 1) / kRedThreads, (size_t)p->red_blocks);
   k_diffnorms<<<blocks, kRedThreads, 0, p->st>>>(a, b, len, p->partial, p->counter, p->scal);
@@ -1177,9 +1286,12 @@ extern "C" int mpbp_wnorms(mpbp_plan* p, const double* a, const double* b, size_
   out3[1] = sqrt(w * p->hscal[1]);  // weighted_L2, utils.py:7-9
   out3[2] = p->hscal[2];            // max_norm,    utils.py:16-17
   return 0;
+  };
+  return leave(p, body());
 }
 extern "C" int mpbp_fill_manufactured(mpbp_plan* p, double* u_vec, double* b_vec, double b_p_sign, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   const Level& v = p->lev[0];
   const mpbp_config& c = p->cfg;
   const dim3 block(128), grid((v.n + 127) / 128, v.rows);
@@ -1187,6 +1299,8 @@ extern "C" int mpbp_fill_manufactured(mpbp_plan* p, double* u_vec, double* b_vec
                                                   b_p_sign);
   LAUNCH_CHECK(p);
   return 0;
+  };
+  return leave(p, body());
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1485,12 +1599,16 @@ static int gmres_dispatch(mpbp_plan* p, const double* b, double* x, const mpbp_g
 extern "C" int mpbp_gmres(mpbp_plan* p, const double* b, double* x, const mpbp_gmres_opts* o, double* hist, int hist_cap,
                           int* n_iters, int* info, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!b || !x || b == x) return set_err(MPBP_E_ARG, "gmres: bad pointers");
   return gmres_dispatch(p, b, x, o, hist, hist_cap, n_iters, info);
+  };
+  return leave(p, body());
 }
 extern "C" int mpbp_gmres_host(mpbp_plan* p, const double* b_host, double* x_host, const mpbp_gmres_opts* o, double* hist,
                                int hist_cap, int* n_iters, int* info, void* stream) {
   ENTER(p, stream);
+  auto body = [&]() -> int {
   if (!b_host || !x_host) return set_err(MPBP_E_ARG, "gmres_host: bad pointers");
   RET(ensure_hostbuf(p));
   const size_t bytes = 5 * p->lev[0].fs() * sizeof(double);
@@ -1500,4 +1618,6 @@ extern "C" int mpbp_gmres_host(mpbp_plan* p, const double* b_host, double* x_hos
   CU(cudaMemcpyAsync(x_host, p->hostbuf_dev[1], bytes, cudaMemcpyDeviceToHost, p->st));
   CU(cudaStreamSynchronize(p->st));
   return 0;
+  };
+  return leave(p, body());
 }

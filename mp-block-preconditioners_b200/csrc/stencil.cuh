@@ -40,12 +40,37 @@ struct VecIn {
   const double* top;
   const double* bot;
   size_t fs, hs;
-  // multi-GPU: the halo rows are pushed into this rank's memory by the ring neighbours (peer stores over
-  // NVLink); blocks that read them first wait until the neighbour's flag reaches `seq` (null: no wait)
+  // multi-GPU: the halo rows are pushed into this rank's comm buffer by the ring neighbours (peer stores
+  // over NVLink).  The exchange sequence number lives on the device (`dseq`, bumped by k_halo_push), so
+  // kernel arguments never change between calls and whole V-cycles replay as CUDA graphs.  A kernel first
+  // resolves slot/top/bot/flags from *dseq; edge warps then wait until the neighbour's flag reaches it.
+  const unsigned long long* dseq;   // null: single GPU / replicated level (top/bot given directly)
+  char* comm;                       // this rank's comm buffer
+  size_t area;                      // doubles per (slot, direction) halo area
   const unsigned long long* flag_top;
   const unsigned long long* flag_bot;
   unsigned long long seq;
 };
+
+// comm buffer layout: 4 flags (slot x {top,bot}), 128 B apart, then [slot][dir][5 fields][n0] doubles
+constexpr size_t kFlagStride = 128;
+constexpr size_t kFlagBytes = 4 * kFlagStride;
+__host__ __device__ __forceinline__ unsigned long long* comm_flag(char* base, int slot, int dir) {
+  return reinterpret_cast<unsigned long long*>(base + (size_t)(slot * 2 + dir) * kFlagStride);
+}
+__host__ __device__ __forceinline__ double* comm_halo(char* base, size_t area, int slot, int dir) {
+  return reinterpret_cast<double*>(base + kFlagBytes) + (size_t)(slot * 2 + dir) * area;
+}
+__device__ __forceinline__ void resolve_halo(VecIn& v) {
+  if (v.dseq == nullptr) return;
+  const unsigned long long s = *v.dseq;
+  const int slot = (int)(s & 1ull);
+  v.seq = s;
+  v.top = comm_halo(v.comm, v.area, slot, 0);
+  v.bot = comm_halo(v.comm, v.area, slot, 1);
+  v.flag_top = comm_flag(v.comm, slot, 0);
+  v.flag_bot = comm_flag(v.comm, slot, 1);
+}
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
@@ -56,8 +81,9 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // warp-level wait for the neighbours' halo rows (called by whole warps; lane 0 polls)
-__device__ __forceinline__ void halo_wait(const VecIn& v, bool need_top, bool need_bot) {
-  if (v.flag_top == nullptr) return;
+__device__ __forceinline__ void halo_wait(VecIn& v, bool need_top, bool need_bot) {
+  if (v.dseq == nullptr) return;
+  resolve_halo(v);
   if ((threadIdx.x & 31) == 0) {
     if (need_top)
       while (ld_acquire_sys(v.flag_top) < v.seq) {
@@ -74,9 +100,12 @@ __device__ __forceinline__ void halo_wait(const VecIn& v, bool need_top, bool ne
 // the last block to finish publishes the flags.  Replaces an ncclSend/ncclRecv pair per field and
 // direction.
 __global__ void __launch_bounds__(256) k_halo_push(const double* __restrict__ x, int nf, size_t fs, int rows, int n,
-                                                   double* __restrict__ prev_bot, double* __restrict__ next_top,
-                                                   unsigned long long* prev_flag_bot, unsigned long long* next_flag_top,
-                                                   unsigned long long seq, unsigned int* done_counter) {
+                                                   char* prev_comm, char* next_comm, size_t area,
+                                                   unsigned long long* dseq, unsigned int* done_counter) {
+  const unsigned long long seq = *dseq + 1ull;  // read before this block's ticket, written only by the last block
+  const int slot = (int)(seq & 1ull);
+  double* __restrict__ prev_bot = comm_halo(prev_comm, area, slot, 1);
+  double* __restrict__ next_top = comm_halo(next_comm, area, slot, 0);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nf * n) {
     const int k = i / n, c = i - k * n;
@@ -91,9 +120,10 @@ __global__ void __launch_bounds__(256) k_halo_push(const double* __restrict__ x,
     const unsigned int t = atomicAdd(done_counter, 1u);
     if (t == gridDim.x - 1) {
       *done_counter = 0u;
+      *dseq = seq;
       __threadfence_system();
-      st_release_sys(prev_flag_bot, seq);
-      st_release_sys(next_flag_top, seq);
+      st_release_sys(comm_flag(prev_comm, slot, 1), seq);
+      st_release_sys(comm_flag(next_comm, slot, 0), seq);
     }
   }
 }
@@ -103,7 +133,16 @@ struct Geo {
   int rows;  // local rows of the slab
   int row0;  // global index of local row 0
   int rs;    // rows per strip (gridDim.y strips)
+  int pf;    // L2 prefetch distance in rows (0 = off)
 };
+
+// Software prefetch into L2 of the row `pf` rows ahead: three lanes (0, 16, 31) cover the <= 3 cache
+// lines a warp's 32 columns touch.  Costs no registers, turns the later LDG into an L2 hit.
+__device__ __forceinline__ void pf_l2(const double* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ bool pf_lane() {
+  const int lane = threadIdx.x & 31;
+  return lane == 0 || lane == 16 || lane == 31;
+}
 
 __device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(kFull, v, 1); }
 __device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(kFull, v, 1); }
@@ -202,6 +241,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_stokes(VecIn xin, const doubl
   if (WITH_P) p_p = row_ptr(xin, 4, r0 + 1, rows, n)[c];
 
   const size_t fs = xin.fs;
+  const bool pfl = pf_lane();
 #pragma unroll 2
   for (int r = r0; r < r1; ++r) {
     // prefetch row r+2 (clamped to r1: the last prefetch is unused but stays in bounds of the halo)
@@ -213,6 +253,19 @@ __global__ void __launch_bounds__(kBlockThreads) k_stokes(VecIn xin, const doubl
     if (WITH_P) p_q = row_ptr(xin, 4, rq, rows, n)[c];
     double bn_u = 0.0, bn_v = 0.0, bs_u = 0.0, bs_v = 0.0;
     const size_t off = (size_t)r * n + c;
+    if (g.pf > 0 && pfl) {
+      const int rp = r + g.pf;
+      if (rp <= r1) {
+        pf_l2(th_row(th, rp, n) + c);
+#pragma unroll
+        for (int k = 0; k < (WITH_P ? 5 : 4); ++k) pf_l2(row_ptr(xin, k, rp, rows, n) + c);
+        if (MODE != 0 && rp < r1) {
+          const size_t offp = (size_t)rp * n + c;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) pf_l2(b + offp + k * fs);
+        }
+      }
+    }
     if (MODE != 0) {
       bn_u = b[off];
       bn_v = b[off + fs];
@@ -319,7 +372,17 @@ __global__ void __launch_bounds__(kBlockThreads) k_jacobi0_F(const double* __res
   const double a_m = th_m + shfl_up1(th_m);
   double a_c = th_c + shfl_up1(th_c);
   double node_c = 0.25 * (a_c + a_m);
+  const bool pfl = pf_lane();
   for (int r = r0; r < r1; ++r) {
+    if (g.pf > 0 && pfl) {
+      const int rp = r + g.pf;
+      if (rp < r1) {
+        pf_l2(th_row(th, rp + 1, n) + c);
+        const size_t offp = (size_t)rp * n + c;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pf_l2(b + offp + k * fs);
+      }
+    }
     const double th_p = th_row(th, r + 1, n)[c];
     const double a_p = th_p + shfl_up1(th_p);
     const double node_p = 0.25 * (a_p + a_c);
