@@ -291,9 +291,14 @@ def run_gpu(args):
         if cpu:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
+        # leave without running CUDA/NCCL teardown from interpreter shutdown (a rank blocking in a
+        # communicator destructor would hang the whole torchrun job)
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def main():

@@ -977,12 +977,16 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
 extern "C" int mpbp_plan_destroy(mpbp_plan* p) {
   if (!p) return 0;
   cudaDeviceSynchronize();
-  if (p->comm_prev) cudaIpcCloseMemHandle(p->comm_prev);
-  if (p->comm_next && p->comm_next != p->comm_prev) cudaIpcCloseMemHandle(p->comm_next);
-  // (destroy is not collective: callers finish all solves on every rank before dropping their plans)
-  if (p->comm) ncclCommDestroy(p->comm);
+  // graphs first: captured NCCL collectives hold references on the communicator, and ncclCommDestroy
+  // waits for them
   for (int i = 0; i < 2; ++i)
     if (p->gexec[i]) cudaGraphExecDestroy(p->gexec[i]);
+  cudaDeviceSynchronize();
+  if (p->comm_prev) cudaIpcCloseMemHandle(p->comm_prev);
+  if (p->comm_next && p->comm_next != p->comm_prev) cudaIpcCloseMemHandle(p->comm_next);
+  // (destroy is not collective: callers finish all solves on every rank before dropping their plans;
+  //  ncclCommAbort never waits for the other ranks)
+  if (p->comm) ncclCommAbort(p->comm);
   if (p->ev_in) cudaEventDestroy(p->ev_in);
   if (p->ev_out) cudaEventDestroy(p->ev_out);
   if (p->own) cudaStreamDestroy(p->own);

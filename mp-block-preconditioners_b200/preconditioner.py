@@ -105,14 +105,21 @@ class Plan:
         self.N = self.rows * self.n  # local cells
         self.kry_ws = None
 
-    def __del__(self):
+    def close(self):
+        """Destroy the native plan now (idempotent)."""
         h = getattr(self, "h", None)
         if h is not None and h.value:
-            try:
-                self.lib.mpbp_plan_destroy(h)
-            except Exception:
-                pass
             self.h = None
+            self.lib.mpbp_plan_destroy(h)
+
+    def __del__(self):
+        import sys
+        if sys is None or sys.is_finalizing():
+            return  # never tear down CUDA/NCCL state from interpreter shutdown
+        try:
+            self.close()
+        except Exception:
+            pass
 
     # ---- helpers -------------------------------------------------------------------------
     def stream(self):
@@ -326,6 +333,12 @@ class MultiphaseBlockPreconditioner:
                                     theta=self.theta, device=self.device, rank=rank, nranks=nranks, nccl_id=nid,
                                     operators_only=operators_only)
         return self._plans[key]
+
+    def close(self):
+        """Destroy all native plans of this object now."""
+        for pl in self._plans.values():
+            pl.close()
+        self._plans.clear()
 
     def get_big_A_matrix(self, c, d_u, d_p: float = 1.0, d_div: float = -1.0):
         """(A, S, F, D, G) as at preconditioner.py:299-349; S is a placeholder (out of scope)."""

@@ -116,9 +116,10 @@ def main():
     krylov_pair("eta1_", 1.0, A1b, M1b, Adb, Mdb, b1b, bdb, ((SIDE_RIGHT, "fgmres"), (SIDE_LEFT, "gmres_left")))
     if rank == 0:
         print("MGPU_ALL_PASS" if ok else "MGPU_FAILED", flush=True)
+    sys.stdout.flush()
     dist.barrier()
-    dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    torch.cuda.synchronize()
+    os._exit(0 if ok else 1)
 
 
 if __name__ == "__main__":
