@@ -57,7 +57,8 @@ static int set_err(int code, const char* fmt, ...) {
 struct Level {
   int n = 0, rows = 0, row0 = 0;
   bool dist = false;  // slab-distributed over ranks (needs halo exchange); false = whole grid on this rank
-  Geo geo{};
+  Geo geo{};   // strip geometry for the register-heavy k_stokes kernels (~5 blocks/SM)
+  Geo geoL{};  // strip geometry for the light kernels (k_poisson, k_div, k_grad, k_jacobi0_F: 12-16 blocks/SM)
   Phys ph{};
   double* th = nullptr;    // padded theta: (rows+2) x n
   double* halo = nullptr;  // [2][5][n] receive rows (dist only)
@@ -113,6 +114,7 @@ struct mpbp_plan {
   cudaStream_t own = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   // V-cycles (rin -> z) replay as CUDA graphs: ~100 small launches per cycle become one graph launch
+  int jac_minb = 0;  // __launch_bounds__ min blocks/SM variant of the Jacobi kernel (register cap)
   bool use_graph = true;
   cudaGraphExec_t gexec[2] = {nullptr, nullptr};
   long long glaunches[2] = {0, 0};
@@ -222,9 +224,27 @@ static void carve(mpbp_plan* p, Bump& B) {
 // ---------------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------------
-static inline dim3 stencil_grid(const Level& v) {
+static inline dim3 stencil_grid(const Level& v, const Geo& g) {
   return dim3((unsigned)((v.n + kWarpCols * kBlockWarps - 1) / (kWarpCols * kBlockWarps)),
-              (unsigned)((v.rows + v.geo.rs - 1) / v.geo.rs));
+              (unsigned)((v.rows + g.rs - 1) / g.rs));
+}
+// Rows per strip: long strips amortise the two re-read halo rows, but the block count should fill whole
+// waves of `cap` resident blocks (wave quantisation costs up to 2x on the slab sizes of 4-8 GPUs).
+static int choose_rs(int gx, int rows, int cap) {
+  if (rows <= 8) return rows;
+  const int s32 = (rows + 31) / 32;
+  if ((long long)gx * s32 >= 4LL * cap) return 32;
+  double best = -1.0;
+  int best_rs = std::min(rows, 32);
+  for (int rs = 4; rs <= std::min(rows, 64); ++rs) {
+    const int S = (rows + rs - 1) / rs;
+    const long long B = (long long)gx * S;
+    const long long waves = (B + cap - 1) / cap;
+    const double eff = (double)B / (double)(waves * cap);
+    const double score = eff * (double)rs / (double)(rs + 2);  // halo rows re-read per strip
+    if (score > best + 1e-12) best = score, best_rs = rs;
+  }
+  return best_rs;
 }
 static inline int ew_blocks(size_t len) { return (int)std::min<size_t>((len + 255) / 256, 148 * 16); }
 
@@ -297,13 +317,17 @@ static int op_stokes(mpbp_plan* p, int l, int mode, bool with_p, const double* x
   Level& v = p->lev[l];
   VecIn in{};
   RET(make_view(p, v, x, with_p ? 5 : 4, in));
-  const dim3 grid = stencil_grid(v), block(kBlockThreads);
+  const dim3 grid = stencil_grid(v, v.geo), block(kBlockThreads);
   if (with_p)
     k_stokes<0, true><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega);
   else if (mode == 0)
     k_stokes<0, false><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega);
   else if (mode == 1)
     k_stokes<1, false><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega);
+  else if (p->jac_minb == 6)
+    k_stokes<2, false, 6><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega);
+  else if (p->jac_minb == 7)
+    k_stokes<2, false, 7><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega);
   else
     k_stokes<2, false><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega);
   LAUNCH_CHECK(p);
@@ -311,7 +335,7 @@ static int op_stokes(mpbp_plan* p, int l, int mode, bool with_p, const double* x
 }
 static int op_jacobi0_F(mpbp_plan* p, int l, const double* b, double* y, double omega) {
   Level& v = p->lev[l];
-  k_jacobi0_F<<<stencil_grid(v), kBlockThreads, 0, p->st>>>(v.th, b, y, v.fs(), v.geo, v.ph, omega);
+  k_jacobi0_F<<<stencil_grid(v, v.geoL), kBlockThreads, 0, p->st>>>(v.th, b, y, v.fs(), v.geoL, v.ph, omega);
   LAUNCH_CHECK(p);
   return 0;
 }
@@ -319,12 +343,12 @@ static int op_poisson(mpbp_plan* p, int l, int mode, const double* x, const doub
   Level& v = p->lev[l];
   VecIn in{};
   if (mode != 3) RET(make_view(p, v, x, 1, in));
-  const dim3 grid = stencil_grid(v), block(kBlockThreads);
+  const dim3 grid = stencil_grid(v, v.geoL), block(kBlockThreads);
   switch (mode) {
-    case 0: k_poisson<0><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega); break;
-    case 1: k_poisson<1><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega); break;
-    case 2: k_poisson<2><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega); break;
-    default: k_poisson<3><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega); break;
+    case 0: k_poisson<0><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geoL, v.ph, omega); break;
+    case 1: k_poisson<1><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geoL, v.ph, omega); break;
+    case 2: k_poisson<2><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geoL, v.ph, omega); break;
+    default: k_poisson<3><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geoL, v.ph, omega); break;
   }
   LAUNCH_CHECK(p);
   return 0;
@@ -336,7 +360,7 @@ static int op_div(mpbp_plan* p, int l, const double* w, const double* add, doubl
   RET(make_view(p, v, w, 4, in));
   Phys ph = v.ph;
   ph.inv_h *= scale;
-  k_div<<<stencil_grid(v), kBlockThreads, 0, p->st>>>(in, v.th, add, r, v.geo, ph);
+  k_div<<<stencil_grid(v, v.geoL), kBlockThreads, 0, p->st>>>(in, v.th, add, r, v.geoL, ph);
   LAUNCH_CHECK(p);
   return 0;
 }
@@ -344,7 +368,7 @@ static int op_grad(mpbp_plan* p, int l, const double* pr, double* y) {
   Level& v = p->lev[l];
   VecIn in{};
   RET(make_view(p, v, pr, 1, in));
-  k_grad<<<stencil_grid(v), kBlockThreads, 0, p->st>>>(in, v.th, y, v.fs(), v.geo, v.ph);
+  k_grad<<<stencil_grid(v, v.geoL), kBlockThreads, 0, p->st>>>(in, v.th, y, v.fs(), v.geoL, v.ph);
   LAUNCH_CHECK(p);
   return 0;
 }
@@ -868,6 +892,7 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
     return fail(set_err(999, "stream/event creation failed"));
   p->st = p->own;
   if (const char* e = getenv("MPBP_GRAPH")) p->use_graph = atoi(e) != 0;
+  if (const char* e = getenv("MPBP_JAC_MINB")) p->jac_minb = atoi(e);
   if (cudaMemsetAsync(p->counter, 0, 64 * sizeof(unsigned int), nullptr) != cudaSuccess ||
       cudaMemsetAsync(p->dseq, 0, 16 * sizeof(unsigned long long), nullptr) != cudaSuccess)
     return fail(set_err(999, "memset failed"));
@@ -947,13 +972,20 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
       v.geo.n = n;
       v.geo.rows = v.rows;
       v.geo.row0 = v.row0;
-      int rs = 32;
       const int gx = (n + kWarpCols * kBlockWarps - 1) / (kWarpCols * kBlockWarps);
-      while (rs > 4 && gx * ((v.rows + rs - 1) / rs) < 592) rs /= 2;
-      v.geo.rs = std::max(1, std::min(rs, v.rows));
-      v.geo.pf = 3;  // measured best on B200 at 4096^2 (profiles/r1_pf_sweep.txt)
+      int sms_ = 148;
+      cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, 0);
+      v.geo.rs = choose_rs(gx, v.rows, 5 * sms_);
+      v.geo.pf = 3;  // measured best on B200 at 4096^2 (profiles/r1_tuning.txt)
       if (const char* e = getenv("MPBP_PF")) v.geo.pf = std::max(0, std::min(atoi(e), 64));
       if (const char* e = getenv("MPBP_RS")) v.geo.rs = std::max(1, std::min(atoi(e), v.rows));
+      v.geoL = v.geo;
+      {  // light kernels (16 resident blocks/SM): 32-row strips, halved until the grid has >= 4 blocks per SM
+        int rs = 32;
+        while (rs > 4 && gx * ((v.rows + rs - 1) / rs) < 4 * sms_) rs /= 2;
+        v.geoL.rs = std::max(1, std::min(rs, v.rows));
+      }
+      if (const char* e = getenv("MPBP_RSL")) v.geoL.rs = std::max(1, std::min(atoi(e), v.rows));
     }
   }
   int dev = 0, sms = 148;

@@ -193,8 +193,8 @@ __device__ __forceinline__ LaneGeom lane_geom(int n) {
 //   MODE 1: y = b - F x                                             K2 residual
 //   MODE 2: y = x + omega * (b - F x) / diag(F)                     K3, solve.py:149-159 (damped)
 // ------------------------------------------------------------------------------------------
-template <int MODE, bool WITH_P>
-__global__ void __launch_bounds__(kBlockThreads) k_stokes(VecIn xin, const double* __restrict__ th,
+template <int MODE, bool WITH_P, int MINB = 0>
+__global__ void __launch_bounds__(kBlockThreads, MINB) k_stokes(VecIn xin, const double* __restrict__ th,
                                                           const double* __restrict__ b, double* __restrict__ y,
                                                           Geo g, Phys ph, double omega) {
   const LaneGeom lg = lane_geom(g.n);

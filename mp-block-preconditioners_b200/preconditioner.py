@@ -113,12 +113,12 @@ class Plan:
             self.lib.mpbp_plan_destroy(h)
 
     def __del__(self):
-        import sys
-        if sys is None or sys.is_finalizing():
-            return  # never tear down CUDA/NCCL state from interpreter shutdown
         try:
+            import sys
+            if sys.is_finalizing():
+                return  # never tear down CUDA/NCCL state from interpreter shutdown
             self.close()
-        except Exception:
+        except BaseException:
             pass
 
     # ---- helpers -------------------------------------------------------------------------
