@@ -95,6 +95,57 @@ __global__ void __launch_bounds__(kRedThreads) k_multi_dot(const double* __restr
   }
 }
 
+// One fused step of modified Gram-Schmidt (the `for k: h = dot(v_k, w); w -= h v_k` loop of scipy's gmres /
+// the Arnoldi loop of fgmres):   w <- w - alpha_prev * v_prev ;  out_dot = <v_next, w> ;  out_nrm = ||w||^2
+// (each part optional).  4 vector passes per basis vector instead of 5, and the per-thread summation
+// order is exactly k_multi_dot<1>'s, so the result is bitwise the unfused dot-then-axpy sequence.
+template <bool HAS_PREV, bool HAS_NEXT, bool NRM>
+__global__ void __launch_bounds__(kRedThreads) k_mgs_fused(const double* __restrict__ alpha_dev,
+                                                           const double* __restrict__ v_prev,
+                                                           const double* __restrict__ v_next, double* __restrict__ w,
+                                                           size_t len, double* __restrict__ partial,
+                                                           unsigned int* counter, double* __restrict__ out_dot,
+                                                           double* __restrict__ out_nrm, int post_sqrt) {
+  __shared__ double smem[kRedThreads / 32];
+  double acc = 0.0, accn = 0.0;
+  double al = 0.0;
+  if (HAS_PREV) al = -alpha_dev[0];
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+    double wi = w[i];
+    if (HAS_PREV) {
+      wi = fma(al, v_prev[i], wi);
+      w[i] = wi;
+    }
+    if (HAS_NEXT) acc = fma(v_next[i], wi, acc);
+    if (NRM) accn = fma(wi, wi, accn);
+  }
+  if (HAS_NEXT) {
+    const double s = block_sum(acc, smem);
+    if (threadIdx.x == 0) partial[2 * blockIdx.x] = s;
+  }
+  if (NRM) {
+    const double s = block_sum(accn, smem);
+    if (threadIdx.x == 0) partial[2 * blockIdx.x + 1] = s;
+  }
+  if (!HAS_NEXT && !NRM) return;
+  if (last_block(counter)) {
+    if (HAS_NEXT) {
+      double s = 0.0;
+      for (int bI = threadIdx.x; bI < (int)gridDim.x; bI += blockDim.x) s += partial[2 * bI];
+      s = block_sum(s, smem);
+      if (threadIdx.x == 0) out_dot[0] = s;
+    }
+    if (NRM) {
+      double s = 0.0;
+      for (int bI = threadIdx.x; bI < (int)gridDim.x; bI += blockDim.x) s += partial[2 * bI + 1];
+      s = block_sum(s, smem);
+      if (threadIdx.x == 0) out_nrm[0] = post_sqrt ? sqrt(s) : s;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+  }
+}
+
 // out[0] = sum x  (used for the mean removal, solve.py:260-264)
 __global__ void __launch_bounds__(kRedThreads) k_sum(const double* __restrict__ x, size_t len,
                                                      double* __restrict__ partial, unsigned int* counter,

@@ -114,6 +114,7 @@ struct mpbp_plan {
   cudaStream_t own = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   // V-cycles (rin -> z) replay as CUDA graphs: ~100 small launches per cycle become one graph launch
+  bool fused_mgs = true;
   int jac_minb = 0;  // __launch_bounds__ min blocks/SM variant of the Jacobi kernel (register cap)
   bool use_graph = true;
   cudaGraphExec_t gexec[2] = {nullptr, nullptr};
@@ -502,6 +503,54 @@ static int v_multi_axpy(mpbp_plan* p, const double* V, size_t ld, int nvec, cons
   }
   return 0;
 }
+// Fused modified Gram-Schmidt of w against V_0..V_j:  hd[k] = <V_k, w_k>, w_{k+1} = w_k - hd[k] V_k,
+// nrm_after = ||w_{j+1}||; optionally nrm_before = ||w_0|| (scipy's h0).  All scalars stay on the device.
+static int v_mgs(mpbp_plan* p, const double* V, size_t ld, int j, double* w, size_t len, double* hd, double* nrm_after,
+                 double* nrm_before) {
+  if (!p->fused_mgs) {
+    if (nrm_before) RET(v_nrm2(p, w, len, nrm_before));
+    for (int k = 0; k <= j; ++k) {
+      RET(v_dot(p, V + (size_t)k * ld, w, len, hd + k));
+      k_axpy_dev<<<ew_blocks(len), 256, 0, p->st>>>(hd + k, -1.0, V + (size_t)k * ld, w, len);
+      LAUNCH_CHECK(p);
+    }
+    return v_nrm2(p, w, len, nrm_after);
+  }
+  const int blocks = (int)std::min<size_t>((len + kRedThreads - 1) / kRedThreads, (size_t)p->red_blocks);
+  const int post = p->nranks == 1 ? 1 : 0;
+  auto finish = [&](double* dot, double* nrm) -> int {
+    if (p->nranks > 1) {
+      if (dot) RET(allreduce_scal(p, dot, 1));
+      if (nrm) {
+        RET(allreduce_scal(p, nrm, 1));
+        k_sqrt_inplace<<<1, 32, 0, p->st>>>(nrm, 1);
+        LAUNCH_CHECK(p);
+      }
+    }
+    return 0;
+  };
+  // first: h_0 = <V_0, w> (+ ||w||)
+  if (nrm_before)
+    k_mgs_fused<false, true, true><<<blocks, kRedThreads, 0, p->st>>>(nullptr, nullptr, V, w, len, p->partial, p->counter,
+                                                                      hd, nrm_before, post);
+  else
+    k_mgs_fused<false, true, false><<<blocks, kRedThreads, 0, p->st>>>(nullptr, nullptr, V, w, len, p->partial,
+                                                                       p->counter, hd, nullptr, post);
+  LAUNCH_CHECK(p);
+  RET(finish(hd, nrm_before));
+  for (int k = 1; k <= j; ++k) {
+    k_mgs_fused<true, true, false><<<blocks, kRedThreads, 0, p->st>>>(hd + k - 1, V + (size_t)(k - 1) * ld,
+                                                                      V + (size_t)k * ld, w, len, p->partial, p->counter,
+                                                                      hd + k, nullptr, post);
+    LAUNCH_CHECK(p);
+    RET(finish(hd + k, nullptr));
+  }
+  k_mgs_fused<true, false, true><<<blocks, kRedThreads, 0, p->st>>>(hd + j, V + (size_t)j * ld, nullptr, w, len, p->partial,
+                                                                    p->counter, nullptr, nrm_after, post);
+  LAUNCH_CHECK(p);
+  return finish(nullptr, nrm_after);
+}
+
 // fetch `count` device scalars to the pinned host mirror (synchronises the stream)
 static int fetch_scal(mpbp_plan* p, const double* dev, int count, double* host) {
   CU(cudaMemcpyAsync(host, dev, count * sizeof(double), cudaMemcpyDeviceToHost, p->st));
@@ -893,6 +942,7 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
   p->st = p->own;
   if (const char* e = getenv("MPBP_GRAPH")) p->use_graph = atoi(e) != 0;
   if (const char* e = getenv("MPBP_JAC_MINB")) p->jac_minb = atoi(e);
+  if (const char* e = getenv("MPBP_FUSED_MGS")) p->fused_mgs = atoi(e) != 0;
   if (cudaMemsetAsync(p->counter, 0, 64 * sizeof(unsigned int), nullptr) != cudaSuccess ||
       cudaMemsetAsync(p->dseq, 0, 16 * sizeof(unsigned long long), nullptr) != cudaSuccess)
     return fail(set_err(999, "memset failed"));
@@ -1439,13 +1489,7 @@ static int gmres_left(mpbp_plan* p, const double* b, double* x, const mpbp_gmres
       RET(op_stokes(p, 0, 0, true, vc, nullptr, tmp, 0.0));  // av = A v[col]
       RET(psolve(p, pc, tmp, w, len));                       // w = M av
       // modified Gram-Schmidt with device-resident coefficients: ds[0]=h0, ds[1+k]=h[col][k], ds[col+2]=h1
-      RET(v_nrm2(p, w, len, ds));
-      for (int k = 0; k <= col; ++k) {
-        RET(v_dot(p, V + (size_t)k * len, w, len, ds + 1 + k));
-        k_axpy_dev<<<ew_blocks(len), 256, 0, p->st>>>(ds + 1 + k, -1.0, V + (size_t)k * len, w, len);
-        LAUNCH_CHECK(p);
-      }
-      RET(v_nrm2(p, w, len, ds + col + 2));
+      RET(v_mgs(p, V, len, col, w, len, ds + 1, ds + col + 2, ds));
       k_scale_dev<<<ew_blocks(len), 256, 0, p->st>>>(ds + col + 2, 1, w, vn, len);
       LAUNCH_CHECK(p);
       RET(fetch_scal(p, ds, col + 3, hs));
@@ -1562,12 +1606,7 @@ static int gmres_right(mpbp_plan* p, const double* b, double* x, const mpbp_gmre
       double* zj = Z + (size_t)j * len;
       RET(psolve(p, pc, vj, zj, len));                       // Z_j = M v_j
       RET(op_stokes(p, 0, 0, true, zj, nullptr, w, 0.0));    // w = A Z_j
-      for (int i = 0; i <= j; ++i) {
-        RET(v_dot(p, V + (size_t)i * len, w, len, ds + i));
-        k_axpy_dev<<<ew_blocks(len), 256, 0, p->st>>>(ds + i, -1.0, V + (size_t)i * len, w, len);
-        LAUNCH_CHECK(p);
-      }
-      RET(v_nrm2(p, w, len, ds + j + 1));
+      RET(v_mgs(p, V, len, j, w, len, ds, ds + j + 1, nullptr));
       k_scale_dev<<<ew_blocks(len), 256, 0, p->st>>>(ds + j + 1, 1, w, V + (size_t)(j + 1) * len, len);
       LAUNCH_CHECK(p);
       RET(fetch_scal(p, ds, j + 2, hs));

@@ -325,6 +325,31 @@ def test_blas1_kernels(mp):
     assert len(vals) == 1
 
 
+def test_fused_mgs_and_graph_replay_are_bitwise_neutral(mp, monkeypatch):
+    """The fused Gram-Schmidt kernel and the CUDA-graph replay of V-cycles are pure scheduling changes:
+    residual histories and iterates must be bit-identical to the unfused / eager execution."""
+    n, xi, eta_n, eta_s, c, d = 64, 1.0, 100.0, 1.0, 1, -1
+    res = {}
+    for tag, env in (("default", {}), ("plain", {"MPBP_FUSED_MGS": "0", "MPBP_GRAPH": "0"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        A, b_vec, u_vec = mp.main(n=n, c=c, d=d, xi=xi, eta_n=eta_n, eta_s=eta_s)
+        bp = mp.MultiphaseBlockPreconditioner(n, xi, eta_n, eta_s)
+        A = bp.get_big_A_matrix(c=c, d_u=d)[0]
+        M = bp.approx_schur_operator(c=c, d_u=d)
+        xr, ir = mp.fgmres(A, b_vec, M=M, tol=1e-8, maxiter=60)
+        hr = mp.fgmres.last_history.copy()
+        xl, il = mp.gmres(A, b_vec, M=M, rtol=1e-8, restart=20, maxiter=10)
+        hl = mp.gmres.last_history.copy()
+        res[tag] = (xr, hr, xl, hl, ir, il)
+        for k in env:
+            monkeypatch.delenv(k)
+    a, b = res["default"], res["plain"]
+    assert a[4] == b[4] == 0
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])
+    assert np.array_equal(a[3], b[3]) and np.array_equal(a[2], b[2])
+
+
 def test_error_behaviour(mp):
     from mp_block_preconditioners_b200._cabi import MpbpError
     bp = mp.MultiphaseBlockPreconditioner(16, 1.0, 1.0, 1.0)
