@@ -7,7 +7,7 @@ metric) with the roofline of the dominant kernel and the CPU oracle timed beside
 
 A "step" is one inner iteration of right-preconditioned FGMRES (solve.py:285): one preconditioner apply
 (approx_schur_op, solve.py:257-277), one A.x, and the Arnoldi orthogonalisation at that basis size
-(restart 20).  Workload: 2D 4096^2 MAC grid, 10^4 viscosity contrast (BASELINE.json configs[3]).
+(restart 40).  Workload: 2D 4096^2 MAC grid, 10^4 viscosity contrast (BASELINE.json configs[3]).
 """
 import argparse
 import json
@@ -20,8 +20,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(n=4096, eta_n=1.0e4, eta_s=1.0, xi=1.0, c=1.0, d_u=-1.0, restart=20)
-SUB = dict(kind="mg", F_cycles=4, P_cycles=2, cheb=True, nu1=2, nu2=2, omega=0.8, n_coarse=4)
+WORKLOAD = dict(n=4096, eta_n=1.0e4, eta_s=1.0, xi=1.0, c=1.0, d_u=-1.0, restart=40)
+# F: 6 / GtG: 2 Chebyshev-accelerated V(2,2) cycles: the configuration that converges at 4096^2, contrast 1e4
+# (40 iterations to rtol 1e-8, profiles/r1_solve_configs.json; with 4 F-cycles it needs 318)
+SUB = dict(kind="mg", F_cycles=6, P_cycles=2, cheb=True, nu1=2, nu2=2, omega=0.8, n_coarse=4)
 METRIC = "gmres_iterations_per_second"
 UNIT = "its/s"
 
@@ -89,7 +91,7 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 def cpu_port_its_per_s(steps, warmup, n_sample=512):
     """Times `steps` FGMRES iterations of the oracle on an n_sample^2 grid (same contrast, same
-    sub-solver definition, restart 20) and scales its/s to the 4096^2 workload by the cell ratio."""
+    sub-solver definition and restart) and scales its/s to the 4096^2 workload by the cell ratio."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import mpbp_oracle as O
@@ -230,7 +232,10 @@ def run_gpu(args):
     jac_bytes = 104.0 * N
     roof = {"bound": "hbm", "kernel": "k_stokes<2,false> (damped-Jacobi sweep on F, level 0)",
             "achieved": jac_bytes / (ms_jac * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
-            "bytes_per_launch": jac_bytes, "ms_per_launch": ms_jac, "traffic": None}
+            "bytes_per_launch": jac_bytes, "ms_per_launch": ms_jac,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 4096^2 on one GPU (ncu --set full,
+            # profiles/r1_ncu_k_stokes_jacobi.txt): 1.2557 GB + 0.5139 GB = 1.014 x the algorithmic bytes
+            "traffic": 1.7696e9 if (world == 1 and n == 4096) else None}
     roof["frac"] = roof["achieved"] / peak
 
     # ---- the preconditioner apply as a whole and the other hot kernels ----
@@ -258,6 +263,7 @@ def run_gpu(args):
     # ---- end to end through the public Python API with HOST buffers: one FGMRES cycle per call ----
     del xF, z
     e2e_calls = max(1, min(2, args.steps // restart))
+    torch.cuda.empty_cache()
     bh = torch.empty(5 * N, dtype=torch.float64, pin_memory=True)
     bh.copy_(b_dev)
     b_host = bh.numpy()

@@ -73,7 +73,24 @@ __global__ void __launch_bounds__(kRedThreads) k_multi_dot(const double* __restr
 #pragma unroll
   for (int k = 0; k < NV; ++k) acc[k] = 0.0;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (NV <= 2) {
+    // four independent loads in flight per stream; the accumulation order is the plain loop's
+    for (; i + 3 * stride < len; i += 4 * stride) {
+      double wv[4], vv[NV][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) wv[u] = w[i + u * stride];
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) vv[k][u] = V[k * ld + i + u * stride];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] = fma(vv[k][u], wv[u], acc[k]);
+    }
+  }
+  for (; i < len; i += stride) {
     const double wi = w[i];
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc[k] = fma(V[k * ld + i], wi, acc[k]);
@@ -111,7 +128,31 @@ __global__ void __launch_bounds__(kRedThreads) k_mgs_fused(const double* __restr
   double al = 0.0;
   if (HAS_PREV) al = -alpha_dev[0];
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < len; i += 4 * stride) {  // four independent loads per stream in flight
+    double wv[4], pv[4], nv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) wv[u] = w[i + u * stride];
+    if (HAS_PREV) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) pv[u] = v_prev[i + u * stride];
+    }
+    if (HAS_NEXT) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) nv[u] = v_next[i + u * stride];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      double wi = wv[u];
+      if (HAS_PREV) {
+        wi = fma(al, pv[u], wi);
+        w[i + u * stride] = wi;
+      }
+      if (HAS_NEXT) acc = fma(nv[u], wi, acc);
+      if (NRM) accn = fma(wi, wi, accn);
+    }
+  }
+  for (; i < len; i += stride) {
     double wi = w[i];
     if (HAS_PREV) {
       wi = fma(al, v_prev[i], wi);

@@ -1041,7 +1041,7 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  p->red_blocks = std::min(kMaxRedBlocks, sms * 4);
+  p->red_blocks = std::min(kMaxRedBlocks, sms * 8);
   if (const char* rb = getenv("MPBP_RED_BLOCKS")) {  // testing knob: changes the (deterministic) summation order
     const int v = atoi(rb);
     if (v >= 1 && v <= kMaxRedBlocks) p->red_blocks = v;
