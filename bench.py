@@ -19,6 +19,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# rank 0 must print exactly ONE line (the JSON): NCCL writes its "NCCL version ..." banner (NCCL_DEBUG=VERSION/WARN)
+# to stdout unless told otherwise, so route NCCL's log to stderr before any communicator exists
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 WORKLOAD = dict(n=4096, eta_n=1.0e4, eta_s=1.0, xi=1.0, c=1.0, d_u=-1.0, restart=40)
 # F: 6 / GtG: 2 Chebyshev-accelerated V(2,2) cycles: the configuration that converges at 4096^2, contrast 1e4
@@ -134,7 +137,7 @@ def run_reference(args):
             "config": config_dict(args.gpus), "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(line)
 
 
 def config_dict(ngpu):
@@ -296,7 +299,7 @@ def run_gpu(args):
                 "roofline": roof, "kernels": kernels, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
         if cpu:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+        _emit(line)
     sys.stdout.flush()
     sys.stderr.flush()
     if world > 1:
@@ -305,6 +308,27 @@ def run_gpu(args):
         dist.barrier()
         torch.cuda.synchronize()
         os._exit(0)
+
+
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    """Everything any library prints to fd 1 during the run (NCCL banners, warnings) goes to stderr; the one
+    JSON line is written to the real stdout by _emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -316,6 +340,7 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="override the grid size (debugging only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    _capture_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
