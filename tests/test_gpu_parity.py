@@ -325,6 +325,33 @@ def test_blas1_kernels(mp):
     assert len(vals) == 1
 
 
+def test_user_supplied_theta_field(mp):
+    """General (non-analytic) cell-centred theta_n input: the mass term then uses two-cell face
+    averages.  Operators, sub-solves and the preconditioner vs the oracle built from the same field."""
+    n, xi, eta_n, eta_s, c, d = 32, 0.9, 20.0, 1.5, 1.2, -1.0
+    r = (np.arange(n) + 0.5)[:, None] / n
+    cc = (np.arange(n) + 0.5)[None, :] / n
+    theta = 0.5 + 0.3 * np.sin(2 * np.pi * (cc + 2 * r)) * np.cos(4 * np.pi * cc) + 0.05 * np.cos(6 * np.pi * r)
+    ops = O.Operators(n, xi, eta_n, eta_s, c, d, theta=theta, mass="average")
+    sub = mp.SubSolver(kind="mg", F_cycles=3, P_cycles=2, cheb=True)
+    bp = mp.MultiphaseBlockPreconditioner(n, xi, eta_n, eta_s, sub_solver=sub, theta=theta)
+    A, S, F, D, G = bp.get_big_A_matrix(c, d)
+    GtG, GtFG, Finv, Pinv = bp.derived_operators(c, d)
+    M = bp.approx_schur_operator(c, d)
+    rng = np.random.default_rng(11)
+    N = n * n
+    x = rng.standard_normal(5 * N)
+    x[4 * N:] -= x[4 * N:].mean()
+    assert relerr(A @ x, ops.A @ x) < 1e-13
+    assert relerr(GtFG @ x[4 * N:], ops.GtFG @ x[4 * N:]) < 1e-12
+    Mo = O.ApproxSchur(ops, O.SubSolverConfig(kind="mg", cycles=3, cheb=True))
+    cfgP = O.SubSolverConfig(kind="mg", cycles=2, cheb=True)
+    Mo.P_inv = O.SubSolver(ops, "P", cfgP, O.Multigrid(ops, cfgP))
+    assert relerr(Finv @ x[:4 * N], Mo.F_inv @ x[:4 * N]) < 1e-10
+    assert relerr(Pinv @ x[4 * N:], Mo.P_inv @ x[4 * N:]) < 1e-10
+    assert relerr(M @ x, Mo.matvec(x)) < 1e-9
+
+
 def test_fused_mgs_and_graph_replay_are_bitwise_neutral(mp, monkeypatch):
     """The fused Gram-Schmidt kernel and the CUDA-graph replay of V-cycles are pure scheduling changes:
     residual histories and iterates must be bit-identical to the unfused / eager execution."""
