@@ -65,6 +65,7 @@ struct Level {
   double *bF = nullptr, *xF = nullptr, *tF = nullptr, *rF = nullptr;  // 4*rows*n each
   double *bP = nullptr, *xP = nullptr, *tP = nullptr, *rP = nullptr;  // rows*n each
   double *gF = nullptr, *gP = nullptr;  // restricted slab before the all-gather (first replicated level only)
+  double* wdF = nullptr;                // omega / diag(F), 4N (whole-grid levels; fused pre-smoothing)
   size_t fs() const { return (size_t)rows * n; }
 };
 
@@ -114,6 +115,9 @@ struct mpbp_plan {
   cudaStream_t own = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   // V-cycles (rin -> z) replay as CUDA graphs: ~100 small launches per cycle become one graph launch
+  // bit 0: fused pre-smoothing pair (default: -10 % V-cycle time), bit 1: fused prolongation + first post-sweep
+  // (128 registers, measured slower: off) -- whole-grid levels only, MPBP_FUSE overrides
+  int fuse = 1;
   bool fused_mgs = true;
   int jac_minb = 0;  // __launch_bounds__ min blocks/SM variant of the Jacobi kernel (register cap)
   bool use_graph = true;
@@ -187,6 +191,7 @@ static void carve(mpbp_plan* p, Bump& B) {
       v.bP = B.take<double>(fs);
       v.xP = B.take<double>(fs);
     }
+    if (!v.dist && l < L - 1 && !p->cfg.operators_only) v.wdF = B.take<double>(4 * fs);
     if (l == p->first_repl) {
       const Level& f = p->lev[l - 1];
       v.gF = B.take<double>(4 * (f.fs() / 4));
@@ -337,6 +342,29 @@ static int op_stokes(mpbp_plan* p, int l, int mode, bool with_p, const double* x
 static int op_jacobi0_F(mpbp_plan* p, int l, const double* b, double* y, double omega) {
   Level& v = p->lev[l];
   k_jacobi0_F<<<stencil_grid(v, v.geoL), kBlockThreads, 0, p->st>>>(v.th, b, y, v.fs(), v.geoL, v.ph, omega);
+  LAUNCH_CHECK(p);
+  return 0;
+}
+// fused smoothing kernels (whole-grid levels only): variant 0 = two pre-smoothing sweeps from zero out of b,
+// variant 1 = x + P e_c followed by one sweep
+static int op_stokes_fused(mpbp_plan* p, int l, int variant, const double* x, const double* b, double* y,
+                           double omega) {
+  Level& v = p->lev[l];
+  if (v.dist) return set_err(MPBP_E_STATE, "internal: fused smoothing on a distributed level");
+  VecIn in{};
+  RET(make_view(p, v, x, 4, in));
+  FuseArgs fa{};
+  if (variant == 0) {
+    RET(make_view(p, v, v.wdF, 4, fa.wd));
+  } else {
+    fa.ec = p->lev[l + 1].xF;
+  }
+  fa.nc = v.n / 2;
+  const dim3 grid = stencil_grid(v, v.geo), block(kBlockThreads);
+  if (variant == 0)
+    k_stokes_fused<0><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega, fa);
+  else
+    k_stokes_fused<1><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega, fa);
   LAUNCH_CHECK(p);
   return 0;
 }
@@ -592,20 +620,35 @@ static int vcycle(mpbp_plan* p, int l, bool isF, const double* b, double* x) {
   const int S = (c.nu1 - 1) + c.nu2;
   double* cur = (S % 2 == 0) ? x : t;
   double* oth = (cur == x) ? t : x;
-  if (isF) RET(op_jacobi0_F(p, l, b, cur, c.omega));
-  else RET(op_poisson(p, l, 3, nullptr, b, cur, c.omega));
-  for (int s = 1; s < c.nu1; ++s) {
-    if (isF) RET(op_stokes(p, l, 2, false, cur, b, oth, c.omega));
-    else RET(op_poisson(p, l, 2, cur, b, oth, c.omega));
+  const bool fuse_pre = isF && (p->fuse & 1) && !v.dist && c.nu1 == 2 && v.wdF != nullptr;
+  const bool fuse_post = isF && (p->fuse & 2) && !v.dist && c.nu2 >= 1;
+  if (fuse_pre) {
+    // x2 straight from b: lands where the unfused jacobi0 + sweep would have left it
+    RET(op_stokes_fused(p, l, 0, b, b, oth, c.omega));
     std::swap(cur, oth);
+  } else {
+    if (isF) RET(op_jacobi0_F(p, l, b, cur, c.omega));
+    else RET(op_poisson(p, l, 3, nullptr, b, cur, c.omega));
+    for (int s = 1; s < c.nu1; ++s) {
+      if (isF) RET(op_stokes(p, l, 2, false, cur, b, oth, c.omega));
+      else RET(op_poisson(p, l, 2, cur, b, oth, c.omega));
+      std::swap(cur, oth);
+    }
   }
   if (isF) RET(op_stokes(p, l, 1, false, cur, b, r, 0.0));
   else RET(op_poisson(p, l, 1, cur, b, r, 0.0));
   RET(op_restrict(p, l, isF, r));
   Level& cl = p->lev[l + 1];
   RET(vcycle(p, l + 1, isF, isF ? cl.bF : cl.bP, isF ? cl.xF : cl.xP));
-  RET(op_prolong_add(p, l, isF, cur));
-  for (int s = 0; s < c.nu2; ++s) {
+  int post = c.nu2;
+  if (fuse_post) {
+    RET(op_stokes_fused(p, l, 1, cur, b, oth, c.omega));
+    std::swap(cur, oth);
+    post--;
+  } else {
+    RET(op_prolong_add(p, l, isF, cur));
+  }
+  for (int s = 0; s < post; ++s) {
     if (isF) RET(op_stokes(p, l, 2, false, cur, b, oth, c.omega));
     else RET(op_poisson(p, l, 2, cur, b, oth, c.omega));
     std::swap(cur, oth);
@@ -943,6 +986,7 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
   if (const char* e = getenv("MPBP_GRAPH")) p->use_graph = atoi(e) != 0;
   if (const char* e = getenv("MPBP_JAC_MINB")) p->jac_minb = atoi(e);
   if (const char* e = getenv("MPBP_FUSED_MGS")) p->fused_mgs = atoi(e) != 0;
+  if (const char* e = getenv("MPBP_FUSE")) p->fuse = atoi(e);
   if (cudaMemsetAsync(p->counter, 0, 64 * sizeof(unsigned int), nullptr) != cudaSuccess ||
       cudaMemsetAsync(p->dseq, 0, 16 * sizeof(unsigned long long), nullptr) != cudaSuccess)
     return fail(set_err(999, "memset failed"));
@@ -1049,6 +1093,16 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
   if (!cfg->operators_only) {
     rc = build_coarse_inverses(p);
     if (rc) return fail(rc);
+    // omega / diag(F) per whole-grid level: one first-sweep kernel applied to a vector of ones
+    for (size_t l = 0; l + 1 < p->lev.size(); ++l) {
+      Level& v = p->lev[l];
+      if (!v.wdF) continue;
+      const size_t len = 4 * v.fs();
+      k_fill<<<ew_blocks(len), 256, 0, p->st>>>(v.tF, 1.0, len);
+      p->launches++;
+      rc = op_jacobi0_F(p, (int)l, v.tF, v.wdF, cfg->omega);
+      if (rc) return fail(rc);
+    }
   }
   if (cudaDeviceSynchronize() != cudaSuccess) return fail(set_err(999, "plan setup failed: %s", cudaGetErrorString(cudaGetLastError())));
   p->launches = 0;
@@ -1255,8 +1309,14 @@ static double vcycle_bytes(const mpbp_plan* p, int l, bool isF) {
   if (l == L - 1) return 0.0;  // dense coarse solve: negligible
   double by = 0.0;
   if (isF) {
-    by += 72 * N;                          // first sweep from x=0
-    by += (c.nu1 - 1 + c.nu2) * 104.0 * N; // Jacobi sweeps
+    const bool fuse_pre = (p->fuse & 1) && !p->lev[l].dist && c.nu1 == 2 && p->lev[l].wdF != nullptr;
+    if (fuse_pre) {
+      by += 104 * N;                         // both pre-smoothing sweeps in one pass (reads b, omega/diag, theta)
+      by += c.nu2 * 104.0 * N;               // post-smoothing sweeps
+    } else {
+      by += 72 * N;                          // first sweep from x=0
+      by += (c.nu1 - 1 + c.nu2) * 104.0 * N; // Jacobi sweeps
+    }
     by += 104 * N;                         // residual
     by += 40 * N;                          // restrict (read 4N, write N)
     by += 72 * N;                          // prolong + correct (read 4N + N, write 4N)

@@ -352,6 +352,166 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) k_stokes(VecIn xin, const
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused smoothing kernels for whole-grid (non slab-distributed) levels.  Same marching structure as
+// k_stokes<2,false>; the difference is how a value of the iterate enters the register window:
+//   V = 0  pre-smoothing pair from a zero guess in ONE pass:  x1 = wd * b (wd = omega/diag(F), precomputed),
+//          x2 = x1 + wd * (b - F x1).  Replaces k_jacobi0_F + one k_stokes<2,false> sweep: reads b, wd, theta
+//          and writes x2 (104N B) instead of 72N + 104N B.
+//   V = 1  coarse-grid correction + first post-smoothing sweep in ONE pass:  xt = x + P e_c (P = 4 R^T),
+//          x_new = xt + omega (b - F xt)/diag.  Replaces k_prolong_add_F (72N B) + one sweep.
+// ------------------------------------------------------------------------------------------
+struct FuseArgs {
+  VecIn wd;          // V = 0: omega / diag(F), 4 fields, viewed with the same periodic wrap as the rhs
+  const double* ec;  // V = 1: coarse correction, 4 fields of nc x nc
+  int nc;
+};
+
+template <int V>
+__global__ void __launch_bounds__(kBlockThreads, V == 0 ? 5 : 4) k_stokes_fused(VecIn xin, const double* __restrict__ th,
+                                                                const double* __restrict__ b, double* __restrict__ y,
+                                                                Geo g, Phys ph, double omega, FuseArgs fa) {
+  const LaneGeom lg = lane_geom(g.n);
+  if (!lg.alive) return;
+  const int n = g.n, rows = g.rows, c = lg.cc;
+  const int r0 = blockIdx.y * g.rs;
+  const int r1 = min(r0 + g.rs, rows);
+  if (r0 >= rows) return;
+  const int nc = fa.nc;
+  const int C = c >> 1, Cp = (C + 1 == nc) ? 0 : C + 1;
+  const bool codd = (c & 1) != 0;
+
+  auto ldx = [&](int k, int row) -> double {
+    const double raw = row_ptr(xin, k, row, rows, n)[c];
+    if (V == 0) return raw * row_ptr(fa.wd, k, row, rows, n)[c];
+    const int fr = row < 0 ? row + rows : (row >= rows ? row - rows : row);  // whole grid on this rank: periodic
+    const int R = fr >> 1;
+    const double* e = fa.ec + (size_t)k * nc * nc;
+    double pe;
+    if ((k & 1) == 0) {  // u-type field: linear in x, constant in y
+      const double* er = e + (size_t)R * nc;
+      pe = codd ? 0.5 * (er[C] + er[Cp]) : er[C];
+    } else {             // v-type field: linear in y, constant in x
+      pe = e[(size_t)R * nc + C];
+      if (fr & 1) {
+        const int Rp = (R + 1 == nc) ? 0 : R + 1;
+        pe = 0.5 * (pe + e[(size_t)Rp * nc + C]);
+      }
+    }
+    return raw + pe;
+  };
+
+  double sxf = 0.0, sxc = 0.0;
+  if (ph.mass_mode) {
+    sxf = ph.sxf[c];
+    sxc = ph.sxc[c];
+  }
+  double th_m = th_row(th, r0 - 1, n)[c];
+  double th_c = th_row(th, r0, n)[c];
+  double un_m = ldx(0, r0 - 1), vn_m = ldx(1, r0 - 1), us_m = ldx(2, r0 - 1), vs_m = ldx(3, r0 - 1);
+  double un_c = ldx(0, r0), vn_c = ldx(1, r0), us_c = ldx(2, r0), vs_c = ldx(3, r0);
+  const double a_m = th_m + shfl_up1(th_m);
+  double a_c = th_c + shfl_up1(th_c);
+  double node_c = 0.25 * (a_c + a_m);
+  double Tn_c = node_c * ((un_m - un_c) + (vn_c - shfl_up1(vn_c)));
+  double Ts_c = (1.0 - node_c) * ((us_m - us_c) + (vs_c - shfl_up1(vs_c)));
+  double Qn_m = th_m * ((shfl_dn1(un_m) - un_m) + (vn_c - vn_m));
+  double Qs_m = (1.0 - th_m) * ((shfl_dn1(us_m) - us_m) + (vs_c - vs_m));
+  double fv_c = 0.5 * (th_c + th_m);
+  double th_p = th_row(th, r0 + 1, n)[c];
+  double un_p = ldx(0, r0 + 1), vn_p = ldx(1, r0 + 1), us_p = ldx(2, r0 + 1), vs_p = ldx(3, r0 + 1);
+
+  const size_t fs = xin.fs;
+  const bool pfl = pf_lane();
+#pragma unroll 2
+  for (int r = r0; r < r1; ++r) {
+    const int rq = min(r + 2, r1);
+    const double th_q = th_row(th, rq, n)[c];
+    const double un_q = ldx(0, rq), vn_q = ldx(1, rq), us_q = ldx(2, rq), vs_q = ldx(3, rq);
+    const size_t off = (size_t)r * n + c;
+    if (g.pf > 0 && pfl) {
+      const int rp = r + g.pf;
+      if (rp <= r1) {
+        pf_l2(th_row(th, rp, n) + c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          pf_l2(row_ptr(xin, k, rp, rows, n) + c);
+          if (V == 0) pf_l2(row_ptr(fa.wd, k, rp, rows, n) + c);
+        }
+        if (V == 1 && rp < r1) {
+          const size_t offp = (size_t)rp * n + c;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) pf_l2(b + offp + k * fs);
+        }
+      }
+    }
+    const double bn_u = b[off], bn_v = b[off + fs], bs_u = b[off + 2 * fs], bs_v = b[off + 3 * fs];
+
+    const double a_p = th_p + shfl_up1(th_p);
+    const double node_p = 0.25 * (a_p + a_c);
+    const double Tn_p = node_p * ((un_c - un_p) + (vn_p - shfl_up1(vn_p)));
+    const double Ts_p = (1.0 - node_p) * ((us_c - us_p) + (vs_p - shfl_up1(vs_p)));
+    const double Qn_c = th_c * ((shfl_dn1(un_c) - un_c) + (vn_p - vn_c));
+    const double Qs_c = (1.0 - th_c) * ((shfl_dn1(us_c) - us_c) + (vs_p - vs_c));
+    const double Lu_n = (Qn_c - shfl_up1(Qn_c)) + (Tn_c - Tn_p);
+    const double Lu_s = (Qs_c - shfl_up1(Qs_c)) + (Ts_c - Ts_p);
+    const double Lv_n = (shfl_dn1(Tn_c) - Tn_c) + (Qn_c - Qn_m);
+    const double Lv_s = (shfl_dn1(Ts_c) - Ts_c) + (Qs_c - Qs_m);
+
+    const double fu_c = 0.5 * a_c;
+    double mu, mv;
+    if (ph.mass_mode) {
+      const int gr = g.row0 + r;
+      mu = 0.25 * sxf * ph.syc[gr] + 0.5;
+      mv = 0.25 * sxc * ph.syf[gr] + 0.5;
+    } else {
+      mu = fu_c;
+      mv = fv_c;
+    }
+    const double dXu = ph.d_u * (ph.xi * fu_c * (1.0 - fu_c));
+    const double dXv = ph.d_u * (ph.xi * fv_c * (1.0 - fv_c));
+    const double du = un_c - us_c, dv = vn_c - vs_c;
+    const double cmu = ph.c * mu, cmv = ph.c * mv;
+    const double F_un = cmu * un_c - dXu * du + ph.kap_n * Lu_n;
+    const double F_us = (ph.c - cmu) * us_c + dXu * du + ph.kap_s * Lu_s;
+    const double F_vn = cmv * vn_c - dXv * dv + ph.kap_n * Lv_n;
+    const double F_vs = (ph.c - cmv) * vs_c + dXv * dv + ph.kap_s * Lv_s;
+    double y_un, y_vn, y_us, y_vs;
+    if (V == 0) {
+      const double* wd = fa.wd.x + off;
+      y_un = un_c + (bn_u - F_un) * wd[0];
+      y_vn = vn_c + (bn_v - F_vn) * wd[fs];
+      y_us = us_c + (bs_u - F_us) * wd[2 * fs];
+      y_vs = vs_c + (bs_v - F_vs) * wd[3 * fs];
+    } else {
+      const double node_e = shfl_dn1(node_c);
+      const double su = a_c + node_c + node_p;
+      const double sv = th_m + th_c + node_c + node_e;
+      y_un = un_c + omega * (bn_u - F_un) * fast_rcp(cmu - dXu - ph.kap_n * su);
+      y_us = us_c + omega * (bs_u - F_us) * fast_rcp((ph.c - cmu) - dXu - ph.kap_s * (4.0 - su));
+      y_vn = vn_c + omega * (bn_v - F_vn) * fast_rcp(cmv - dXv - ph.kap_n * sv);
+      y_vs = vs_c + omega * (bs_v - F_vs) * fast_rcp((ph.c - cmv) - dXv - ph.kap_s * (4.0 - sv));
+    }
+    if (lg.store) {
+      y[off] = y_un;
+      y[off + fs] = y_vn;
+      y[off + 2 * fs] = y_us;
+      y[off + 3 * fs] = y_vs;
+    }
+    th_m = th_c; th_c = th_p; th_p = th_q;
+    a_c = a_p; node_c = node_p;
+    un_c = un_p; vn_c = vn_p; us_c = us_p; vs_c = vs_p;
+    un_p = un_q; vn_p = vn_q; us_p = us_q; vs_p = vs_q;
+    Tn_c = Tn_p; Ts_c = Ts_p; Qn_m = Qn_c; Qs_m = Qs_c;
+    fv_c = 0.5 * (th_c + th_m);
+  }
+}
+
+__global__ void k_fill(double* __restrict__ x, double v, size_t len) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) x[i] = v;
+}
+
 // x = omega * b / diag(F): first Jacobi sweep from a zero initial guess (solve.py:149-159 with x=0)
 __global__ void __launch_bounds__(kBlockThreads) k_jacobi0_F(const double* __restrict__ th, const double* __restrict__ b,
                                                              double* __restrict__ y, size_t fs, Geo g, Phys ph,

@@ -377,6 +377,31 @@ def test_fused_mgs_and_graph_replay_are_bitwise_neutral(mp, monkeypatch):
     assert np.array_equal(a[3], b[3]) and np.array_equal(a[2], b[2])
 
 
+@pytest.mark.parametrize("fuse", ["1", "2", "3"])
+@pytest.mark.parametrize("n,eta_n", [(64, 1e3), (48, 10.0), (16, 100.0)])
+def test_fused_smoothing_kernels_vs_oracle(mp, monkeypatch, fuse, n, eta_n):
+    """MPBP_FUSE bit 0: the two pre-smoothing sweeps in one kernel; bit 1: prolongation + first post-sweep in
+    one kernel.  Same V-cycle, so the oracle tolerances of the unfused path apply."""
+    monkeypatch.setenv("MPBP_FUSE", fuse)
+    xi, eta_s, c, d = 1.0, 1.0, 1.0, -1.0
+    sub = mp.SubSolver(kind="mg", F_cycles=3, P_cycles=2, cheb=True)
+    bp = mp.MultiphaseBlockPreconditioner(n, xi, eta_n, eta_s, sub_solver=sub)
+    p = bp.plan(c, d)
+    monkeypatch.delenv("MPBP_FUSE")
+    ops = O.Operators(n, xi, eta_n, eta_s, c, d)
+    rng = np.random.default_rng(3)
+    N = n * n
+    v = rng.standard_normal(5 * N)
+    v[4 * N:] -= v[4 * N:].mean()
+    mg1 = O.Multigrid(ops, O.SubSolverConfig(kind="mg", cycles=1))
+    assert relerr(p.call("mpbp_vcycle_F", v[:4 * N], 4 * N, 4 * N), mg1._vcycle("F", 0, v[:4 * N])) < 1e-10
+    Mo = O.ApproxSchur(ops, O.SubSolverConfig(kind="mg", cycles=3, cheb=True))
+    cfgP = O.SubSolverConfig(kind="mg", cycles=2, cheb=True)
+    Mo.P_inv = O.SubSolver(ops, "P", cfgP, O.Multigrid(ops, cfgP))
+    M = bp.approx_schur_operator(c, d)
+    assert relerr(M @ v, Mo.matvec(v)) < 1e-9
+
+
 def test_error_behaviour(mp):
     from mp_block_preconditioners_b200._cabi import MpbpError
     bp = mp.MultiphaseBlockPreconditioner(16, 1.0, 1.0, 1.0)
