@@ -78,8 +78,10 @@ def test_slab_level_shapes_multi_rank(lib):
         cfg.nccl_unique_id = C.cast(idbuf, C.c_void_p)
         assert lib.mpbp_plan_workspace_bytes(C.byref(cfg), C.byref(need)) == 0, lib.mpbp_last_error_string()
         sizes[P] = need.value
+    # (slab-distributed levels carry no omega/diag array for the fused pre-smoothing, so a rank's share is a
+    # little below 1/P of the single-GPU workspace)
     for P in (2, 4, 8):
-        assert 0.95 < sizes[P] * P / sizes[1] < 1.10, sizes
+        assert 0.85 < sizes[P] * P / sizes[1] < 1.10, sizes
 
 
 def test_no_gpu_fails_loudly(lib):
