@@ -7,13 +7,13 @@ part of `solve_with_approx_schur_pc` (/root/reference/solve.py:243-254, :280-281
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 import torch
 
 from . import _cabi
-from ._cabi import SIDE_LEFT, SIDE_RIGHT, SUB_JACOBI, SUB_MG, Config, GmresOpts, check
+from ._cabi import SUB_JACOBI, SUB_MG, Config, check
 
 PI = np.pi
 

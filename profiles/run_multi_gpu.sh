@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: gpu_scale2.sh N [check]  -- bounded multi-GPU run: optional parity check at n=2048, then the bench
+# usage: run_multi_gpu.sh N [check]  -- bounded multi-GPU run: optional parity check at n=2048, then the bench
 N=$1
 if [ "$2" = "check" ]; then
 timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 tests/mgpu_check.py 2048 > gpurun_out/mgpu${N}b.log 2>&1
