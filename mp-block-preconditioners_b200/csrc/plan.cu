@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "blas1.cuh"
+#include "coarse.cuh"
 #include "stencil.cuh"
 
 using namespace mpbp;
@@ -118,6 +119,7 @@ struct mpbp_plan {
   // bit 0: fused pre-smoothing pair (default: -10 % V-cycle time), bit 1: fused prolongation + first post-sweep
   // (128 registers, measured slower: off) -- whole-grid levels only, MPBP_FUSE overrides
   int fuse = 1;
+  int coarse_n = 0;  // experimental (MPBP_COARSE=<n>): whole-grid levels with n <= coarse_n run as ONE persistent kernel
   bool fused_mgs = true;
   int jac_minb = 0;  // __launch_bounds__ min blocks/SM variant of the Jacobi kernel (register cap)
   bool use_graph = true;
@@ -605,12 +607,43 @@ static int jacobi_sweeps(mpbp_plan* p, int l, bool isF, const double* b, double*
   return 0;
 }
 
+// experimental: the whole sub-hierarchy from level l down as one single-CTA kernel (csrc/coarse.cuh)
+static int coarse_vcycle_launch(mpbp_plan* p, int l, bool isF, const double* b, double* x) {
+  const int L = (int)p->lev.size();
+  CoarseArgs a{};
+  a.nlev = L - l;
+  for (int i = 0; i < a.nlev; ++i) {
+    Level& v = p->lev[l + i];
+    CoarseLevel& cl = a.lev[i];
+    cl.n = v.n;
+    cl.ph = v.ph;
+    cl.th = v.th;
+    cl.b = isF ? v.bF : v.bP;
+    cl.x = isF ? v.xF : v.xP;
+    cl.t = isF ? v.tF : v.tP;
+    cl.r = isF ? v.rF : v.rP;
+  }
+  a.Minv_t = isF ? p->FinvT : p->PinvT;
+  a.m = isF ? p->mF : p->mP;
+  a.b_in = b;
+  a.x_out = x;
+  a.omega = p->cfg.omega;
+  a.nu1 = p->cfg.nu1;
+  a.nu2 = p->cfg.nu2;
+  if (isF) k_coarse_vcycle<true><<<1, kCoarseThreadsF, 0, p->st>>>(a);
+  else k_coarse_vcycle<false><<<1, kCoarseThreadsP, 0, p->st>>>(a);
+  LAUNCH_CHECK(p);
+  return 0;
+}
+
 // x = V b: one V(nu1,nu2) cycle from a zero guess.  x must not alias the level's t/r buffers.
 static int vcycle(mpbp_plan* p, int l, bool isF, const double* b, double* x) {
   const mpbp_config& c = p->cfg;
   if (c.operators_only) return set_err(MPBP_E_STATE, "plan was created with operators_only");
   Level& v = p->lev[l];
   const int L = (int)p->lev.size();
+  if (p->coarse_n > 0 && !v.dist && v.n <= p->coarse_n && l < L - 1 && (L - l) <= kCoarseMaxLevels)
+    return coarse_vcycle_launch(p, l, isF, b, x);
   if (l == L - 1) {
     // coarsest level: dense inverse (F) / pseudo-inverse (GtG)
     return isF ? op_dense(p, p->FinvT, b, x, p->mF) : op_dense(p, p->PinvT, b, x, p->mP);
@@ -987,6 +1020,7 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
   if (const char* e = getenv("MPBP_JAC_MINB")) p->jac_minb = atoi(e);
   if (const char* e = getenv("MPBP_FUSED_MGS")) p->fused_mgs = atoi(e) != 0;
   if (const char* e = getenv("MPBP_FUSE")) p->fuse = atoi(e);
+  if (const char* e = getenv("MPBP_COARSE")) p->coarse_n = atoi(e);
   if (cudaMemsetAsync(p->counter, 0, 64 * sizeof(unsigned int), nullptr) != cudaSuccess ||
       cudaMemsetAsync(p->dseq, 0, 16 * sizeof(unsigned long long), nullptr) != cudaSuccess)
     return fail(set_err(999, "memset failed"));

@@ -13,7 +13,11 @@
 // no shared memory and no block barrier is needed.  Rows above/below the slab come through the
 // `top`/`bot` halo pointers (periodic wrap on one GPU, neighbour rows after a halo exchange).
 #pragma once
+#ifdef MPBP_EMU  // host-side logic checks of these kernels without a GPU (tests/emu/, test infrastructure only)
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace mpbp {
@@ -72,6 +76,14 @@ __device__ __forceinline__ void resolve_halo(VecIn& v) {
   v.flag_bot = comm_flag(v.comm, slot, 1);
 }
 
+#ifdef MPBP_EMU
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  return *(const volatile unsigned long long*)p;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  *(volatile unsigned long long*)p = v;
+}
+#else
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -80,6 +92,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+#endif
 // warp-level wait for the neighbours' halo rows (called by whole warps; lane 0 polls)
 __device__ __forceinline__ void halo_wait(VecIn& v, bool need_top, bool need_bot) {
   if (v.dseq == nullptr) return;
@@ -138,7 +151,11 @@ struct Geo {
 
 // Software prefetch into L2 of the row `pf` rows ahead: three lanes (0, 16, 31) cover the <= 3 cache
 // lines a warp's 32 columns touch.  Costs no registers, turns the later LDG into an L2 hit.
+#ifdef MPBP_EMU
+__device__ __forceinline__ void pf_l2(const double*) {}
+#else
 __device__ __forceinline__ void pf_l2(const double* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
 __device__ __forceinline__ bool pf_lane() {
   const int lane = threadIdx.x & 31;
   return lane == 0 || lane == 16 || lane == 31;
@@ -157,8 +174,13 @@ __device__ __forceinline__ const double* row_ptr(const VecIn& v, int k, int r, i
 __device__ __forceinline__ const double* th_row(const double* th, int r, int n) { return th + (size_t)(r + 1) * n; }
 
 __device__ __forceinline__ double fast_rcp(double d) {
+#ifdef MPBP_EMU
+  return 1.0 / d;
+#endif
   double r;
+#ifndef MPBP_EMU
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+#endif
   double e = fma(-d, r, 1.0);
   r = fma(r, e, r);
   e = fma(-d, r, 1.0);
@@ -760,6 +782,7 @@ __global__ void k_prolong_add_P(const double* __restrict__ xc, double* __restric
   xf[(size_t)r * nf + c] += xc[(size_t)(r >> 1) * nc + (c >> 1)];
 }
 
+#ifndef MPBP_EMU
 // y = M x for the coarsest-level dense (pseudo-)inverse; Mt is column-major (Mt[k*m+i] = M[i][k])
 __global__ void k_dense_matvec(const double* __restrict__ Mt, const double* __restrict__ x, double* __restrict__ y,
                                int m) {
@@ -772,6 +795,7 @@ __global__ void k_dense_matvec(const double* __restrict__ Mt, const double* __re
     y[i] = acc;
   }
 }
+#endif  // MPBP_EMU
 
 // manufactured solution and right-hand side of solve.main (solve.py:52-78 via utils.py:159-210)
 __global__ void k_fill_manufactured(double* __restrict__ u_vec, double* __restrict__ b_vec, int n, int rows, int row0,

@@ -1,0 +1,91 @@
+"""ctypes front end of the SIMT-on-CPU build of the CUDA kernels (tests/emu/emu_kernels.cpp).
+TEST INFRASTRUCTURE ONLY: logic checks of kernels on the GPU-less build container."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+OUT = os.path.join(HERE, "_build", "libmpbp_emu.so")
+SRCS = [os.path.join(HERE, "emu_kernels.cpp"), os.path.join(HERE, "cuda_emu.h"),
+        os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "stencil.cuh"),
+        os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "coarse.cuh")]
+_dp = C.POINTER(C.c_double)
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(OUT) or any(os.path.getmtime(s) > os.path.getmtime(OUT) for s in SRCS):
+            os.makedirs(os.path.dirname(OUT), exist_ok=True)
+            cmd = ["g++", "-O1", "-std=c++17", "-pthread", "-fPIC", "-shared", "-ffp-contract=off", "-I" + HERE, "-o", OUT, SRCS[0]]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError("g++ failed:\n" + res.stderr[-4000:])
+        _lib = C.CDLL(OUT)
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def pad_theta(theta):
+    """(n+2) x n padded theta (row -1 and row n are the periodic neighbours), the layout plan.cu uploads."""
+    return np.ascontiguousarray(np.concatenate([theta[-1:], theta, theta[:1]], axis=0))
+
+
+def params(xi, eta_n, eta_s, c, d_u, d_p=1.0, d_div=-1.0):
+    return np.array([xi, eta_n, eta_s, c, d_u, d_p, d_div], dtype=np.float64)
+
+
+def stokes(mode, with_p, n, prm, mass_mode, theta, x, b=None, rs=8, pf=3, omega=0.8):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.zeros(5 * n * n if with_p else 4 * n * n)
+    thp = pad_theta(theta)
+    bb = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+    load().emu_stokes(mode, int(with_p), n, _p(prm), mass_mode, _p(thp), _p(x), _p(bb), _p(y), rs, pf, C.c_double(omega))
+    return y
+
+
+def stokes_fused(variant, n, prm, mass_mode, theta, x, b, wd=None, ec=None, rs=8, pf=3, omega=0.8):
+    y = np.zeros(4 * n * n)
+    thp = pad_theta(theta)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    wd = None if wd is None else np.ascontiguousarray(wd, dtype=np.float64)
+    ec = None if ec is None else np.ascontiguousarray(ec, dtype=np.float64)
+    load().emu_stokes_fused(variant, n, _p(prm), mass_mode, _p(thp), _p(x), _p(b), _p(wd), _p(ec), _p(y), rs, pf,
+                            C.c_double(omega))
+    return y
+
+
+def jacobi0_F(n, prm, mass_mode, theta, b, rs=8, omega=0.8):
+    y = np.zeros(4 * n * n)
+    thp = pad_theta(theta)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    load().emu_jacobi0_F(n, _p(prm), mass_mode, _p(thp), _p(b), _p(y), rs, C.c_double(omega))
+    return y
+
+
+def poisson(mode, n, prm, theta, p, b=None, rs=8, omega=0.8):
+    y = np.zeros(n * n)
+    thp = pad_theta(theta)
+    p = None if p is None else np.ascontiguousarray(p, dtype=np.float64)
+    b = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+    load().emu_poisson(mode, n, _p(prm), _p(thp), _p(p), _p(b), _p(y), rs, C.c_double(omega))
+    return y
+
+
+def coarse_vcycle(isF, n, prm, mass_mode, theta, n_coarse, omega, nu1, nu2, Minv, b, threads=256):
+    """Minv: row-major dense (pseudo-)inverse of the coarsest level."""
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.zeros_like(b)
+    Mt = np.ascontiguousarray(Minv.T, dtype=np.float64)  # column-major storage of Minv == row-major of Minv^T
+    th = np.ascontiguousarray(theta, dtype=np.float64)
+    load().emu_coarse_vcycle(int(isF), n, _p(prm), mass_mode, _p(th), n_coarse, C.c_double(omega), nu1, nu2, _p(Mt),
+                             Minv.shape[0], _p(b), _p(x), threads)
+    return x

@@ -1,0 +1,171 @@
+// Host build of the CUDA stencil kernels on the SIMT-on-CPU shim (tests/emu/cuda_emu.h): logic checks of
+// the kernels against the oracle on the GPU-less build container.  TEST INFRASTRUCTURE ONLY.
+#define MPBP_EMU 1
+#include "../../mp-block-preconditioners_b200/csrc/stencil.cuh"
+#include "../../mp-block-preconditioners_b200/csrc/coarse.cuh"
+
+using namespace mpbp;
+
+namespace {
+struct Tables {
+  std::vector<double> sxf, sxc, syf, syc;
+};
+Phys make_phys(int n, double xi, double eta_n, double eta_s, double c, double d_u, double d_p, double d_div,
+               int mass_mode, Tables& t) {
+  const double PI = 3.141592653589793, h = 1.0 / n;
+  t.sxf.resize(n); t.sxc.resize(n); t.syf.resize(n); t.syc.resize(n);
+  for (int i = 0; i < n; ++i) {
+    t.sxf[i] = std::sin(2 * PI * (i * h));
+    t.sxc[i] = std::sin(2 * PI * ((i + 0.5) * h));
+    t.syf[i] = std::sin(2 * PI * (-i * h));
+    t.syc[i] = std::sin(2 * PI * (-(i + 0.5) * h));
+  }
+  Phys ph{};
+  ph.xi = xi; ph.c = c; ph.d_u = d_u;
+  ph.kap_n = d_u * eta_n / (h * h);
+  ph.kap_s = d_u * eta_s / (h * h);
+  ph.dp_h = d_p / h; ph.ddiv_h = d_div / h; ph.inv_h = 1.0 / h; ph.dp_h2 = d_p / (h * h);
+  ph.mass_mode = mass_mode;
+  ph.sxf = t.sxf.data(); ph.sxc = t.sxc.data(); ph.syf = t.syf.data(); ph.syc = t.syc.data();
+  return ph;
+}
+VecIn whole_grid_view(const double* x, int n) {
+  VecIn v{};
+  v.x = x;
+  v.fs = v.hs = (size_t)n * n;
+  v.top = x + (size_t)(n - 1) * n;
+  v.bot = x;
+  return v;
+}
+dim3 sgrid(int n, int rs) { return dim3((n + kWarpCols * kBlockWarps - 1) / (kWarpCols * kBlockWarps), (n + rs - 1) / rs); }
+}  // namespace
+
+extern "C" {
+
+// params: xi, eta_n, eta_s, c, d_u, d_p, d_div ; th_pad: (n+2) x n padded theta
+void emu_stokes(int mode, int with_p, int n, const double* prm, int mass_mode, const double* th_pad, const double* x,
+                const double* b, double* y, int rs, int pf, double omega) {
+  Tables t;
+  const Phys ph = make_phys(n, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], prm[6], mass_mode, t);
+  const Geo g{n, n, 0, rs, pf};
+  const VecIn in = whole_grid_view(x, n);
+  emu::launch(sgrid(n, rs), dim3(kBlockThreads), [&] {
+    if (with_p) k_stokes<0, true>(in, th_pad, b, y, g, ph, omega);
+    else if (mode == 0) k_stokes<0, false>(in, th_pad, b, y, g, ph, omega);
+    else if (mode == 1) k_stokes<1, false>(in, th_pad, b, y, g, ph, omega);
+    else k_stokes<2, false>(in, th_pad, b, y, g, ph, omega);
+  });
+}
+
+void emu_stokes_fused(int variant, int n, const double* prm, int mass_mode, const double* th_pad, const double* x,
+                      const double* b, const double* wd, const double* ec, double* y, int rs, int pf, double omega) {
+  Tables t;
+  const Phys ph = make_phys(n, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], prm[6], mass_mode, t);
+  const Geo g{n, n, 0, rs, pf};
+  const VecIn in = whole_grid_view(x, n);
+  FuseArgs fa{};
+  if (wd) fa.wd = whole_grid_view(wd, n);
+  fa.ec = ec;
+  fa.nc = n / 2;
+  emu::launch(sgrid(n, rs), dim3(kBlockThreads), [&] {
+    if (variant == 0) k_stokes_fused<0>(in, th_pad, b, y, g, ph, omega, fa);
+    else k_stokes_fused<1>(in, th_pad, b, y, g, ph, omega, fa);
+  });
+}
+
+void emu_jacobi0_F(int n, const double* prm, int mass_mode, const double* th_pad, const double* b, double* y, int rs,
+                   double omega) {
+  Tables t;
+  const Phys ph = make_phys(n, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], prm[6], mass_mode, t);
+  const Geo g{n, n, 0, rs, 0};
+  emu::launch(sgrid(n, rs), dim3(kBlockThreads), [&] { k_jacobi0_F(th_pad, b, y, (size_t)n * n, g, ph, omega); });
+}
+
+void emu_poisson(int mode, int n, const double* prm, const double* th_pad, const double* p, const double* b, double* y,
+                 int rs, double omega) {
+  Tables t;
+  const Phys ph = make_phys(n, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], prm[6], 0, t);
+  const Geo g{n, n, 0, rs, 0};
+  const VecIn in = whole_grid_view(p ? p : b, n);
+  emu::launch(sgrid(n, rs), dim3(kBlockThreads), [&] {
+    switch (mode) {
+      case 0: k_poisson<0>(in, th_pad, b, y, g, ph, omega); break;
+      case 1: k_poisson<1>(in, th_pad, b, y, g, ph, omega); break;
+      case 2: k_poisson<2>(in, th_pad, b, y, g, ph, omega); break;
+      default: k_poisson<3>(in, th_pad, b, y, g, ph, omega); break;
+    }
+  });
+}
+
+void emu_transfer(int what, int nf, const double* in_, double* out) {
+  // what: 0 restrict_F (in: fine 4 fields -> out: coarse), 1 prolong_add_F (in: coarse, out: fine, accumulates),
+  //       2 restrict_P, 3 prolong_add_P
+  const int nc = nf / 2;
+  if (what == 0) {
+    const VecIn v = whole_grid_view(in_, nf);
+    emu::launch(dim3((nc + 127) / 128, nc), dim3(128), [&] { k_restrict_F(v, out, nf, nf); });
+  } else if (what == 1) {
+    const VecIn v = whole_grid_view(in_, nc);
+    emu::launch(dim3((nf + 127) / 128, nf), dim3(128), [&] { k_prolong_add_F(v, out, nf, nf); });
+  } else if (what == 2) {
+    emu::launch(dim3((nc + 127) / 128, nc), dim3(128), [&] { k_restrict_P(in_, out, nf, nf); });
+  } else {
+    emu::launch(dim3((nf + 127) / 128, nf), dim3(128), [&] { k_prolong_add_P(in_, out, nf, nf); });
+  }
+}
+
+// persistent coarse V-cycle (csrc/coarse.cuh) on the hierarchy n -> n_coarse built here the way plan.cu builds it
+// (theta averaged 2x2, padded; mass term analytic on the first level only when mass_mode is set)
+void emu_coarse_vcycle(int isF, int n, const double* prm, int mass_mode, const double* theta, int n_coarse,
+                       double omega, int nu1, int nu2, const double* Minv_t, int m, const double* b, double* x,
+                       int threads) {
+  std::vector<Tables> tabs(kCoarseMaxLevels);
+  std::vector<std::vector<double>> th_pad, work;
+  CoarseArgs a{};
+  std::vector<double> th(theta, theta + (size_t)n * n);
+  int cur = n, l = 0;
+  const int nf = isF ? 4 : 1;
+  while (true) {
+    if (l > 0) {
+      const int f = 2 * cur;
+      std::vector<double> tc((size_t)cur * cur);
+      for (int R = 0; R < cur; ++R)
+        for (int C = 0; C < cur; ++C) {
+          const double* q = &th[(size_t)(2 * R) * f + 2 * C];
+          tc[(size_t)R * cur + C] = 0.25 * (q[0] + q[f] + q[1] + q[f + 1]);
+        }
+      th.swap(tc);
+    }
+    th_pad.emplace_back((size_t)(cur + 2) * cur);
+    for (int r = -1; r <= cur; ++r)
+      std::memcpy(&th_pad.back()[(size_t)(r + 1) * cur], &th[(size_t)((r + cur) % cur) * cur], cur * sizeof(double));
+    CoarseLevel& L = a.lev[l];
+    L.n = cur;
+    L.ph = make_phys(cur, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], prm[6], (l == 0) ? mass_mode : 0, tabs[l]);
+    for (int k = 0; k < 4; ++k) work.emplace_back((size_t)nf * cur * cur, 0.0);
+    l++;
+    if (cur <= n_coarse || (cur % 2) || l >= kCoarseMaxLevels) break;
+    cur /= 2;
+  }
+  a.nlev = l;
+  for (int i = 0; i < l; ++i) {
+    a.lev[i].th = th_pad[i].data();
+    a.lev[i].b = work[4 * i].data();
+    a.lev[i].x = work[4 * i + 1].data();
+    a.lev[i].t = work[4 * i + 2].data();
+    a.lev[i].r = work[4 * i + 3].data();
+  }
+  a.Minv_t = Minv_t;
+  a.m = m;
+  a.b_in = b;
+  a.x_out = x;
+  a.omega = omega;
+  a.nu1 = nu1;
+  a.nu2 = nu2;
+  emu::launch(dim3(1), dim3(threads), [&] {
+    if (isF) k_coarse_vcycle<true>(a);
+    else k_coarse_vcycle<false>(a);
+  });
+}
+
+}  // extern "C"

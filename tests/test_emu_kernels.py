@@ -1,0 +1,78 @@
+"""CPU logic checks of the CUDA kernels compiled for the host on a SIMT-on-CPU shim (tests/emu): first the
+GPU-proven marching kernels (this validates the shim itself), then the kernels that have not been on a B200
+yet (the persistent coarse V-cycle of csrc/coarse.cuh).  Small grids only: every CUDA thread is an OS thread."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import mpbp_oracle as O
+from conftest import relerr
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import emu  # noqa: E402
+
+XI, ETA_N, ETA_S, CC, D = 0.9, 30.0, 1.5, 1.1, -1.0
+
+
+def _setup(n, analytic=True):
+    if analytic:
+        theta = O.cell_theta(n)
+        ops = O.Operators(n, XI, ETA_N, ETA_S, CC, D)
+    else:
+        r = (np.arange(n) + 0.5)[:, None] / n
+        c = (np.arange(n) + 0.5)[None, :] / n
+        theta = 0.5 + 0.3 * np.sin(2 * np.pi * (c + 2 * r)) * np.cos(4 * np.pi * c)
+        ops = O.Operators(n, XI, ETA_N, ETA_S, CC, D, theta=theta, mass="average")
+    return theta, ops, emu.params(XI, ETA_N, ETA_S, CC, D)
+
+
+@pytest.mark.parametrize("n,analytic", [(8, True), (12, False)])
+def test_shim_reproduces_gpu_proven_kernels(n, analytic):
+    theta, ops, prm = _setup(n, analytic)
+    mm = 1 if analytic else 0
+    rng = np.random.default_rng(n)
+    N = n * n
+    x = rng.standard_normal(5 * N)
+    b = rng.standard_normal(4 * N)
+    assert relerr(emu.stokes(0, True, n, prm, mm, theta, x, rs=4), ops.A @ x) < 1e-13
+    assert relerr(emu.stokes(0, False, n, prm, mm, theta, x[:4 * N], rs=5), ops.F @ x[:4 * N]) < 1e-13
+    assert relerr(emu.stokes(1, False, n, prm, mm, theta, x[:4 * N], b, rs=4), b - ops.F @ x[:4 * N]) < 1e-13
+    jac = x[:4 * N] + 0.8 * (b - ops.F @ x[:4 * N]) / ops.F.diagonal()
+    assert relerr(emu.stokes(2, False, n, prm, mm, theta, x[:4 * N], b, rs=4), jac) < 1e-13
+    assert relerr(emu.jacobi0_F(n, prm, mm, theta, b, rs=4), 0.8 * b / ops.F.diagonal()) < 1e-13
+    p = x[4 * N:]
+    assert relerr(emu.poisson(0, n, prm, theta, p), ops.GtG @ p) < 1e-13
+    assert relerr(emu.poisson(2, n, prm, theta, p, b[:N]), p + 0.8 * (b[:N] - ops.GtG @ p) / ops.GtG.diagonal()) < 1e-13
+
+
+def test_fused_presmoothing_kernel_logic():
+    n = 8
+    theta, ops, prm = _setup(n, True)
+    rng = np.random.default_rng(1)
+    b = rng.standard_normal(4 * n * n)
+    dg = ops.F.diagonal()
+    x1 = 0.8 * b / dg
+    x2 = x1 + 0.8 * (b - ops.F @ x1) / dg
+    got = emu.stokes_fused(0, n, prm, 1, theta, b, b, wd=0.8 / dg, rs=4)
+    assert relerr(got, x2) < 1e-13
+
+
+@pytest.mark.parametrize("n,analytic,nu", [(8, True, (2, 2)), (16, False, (2, 2)), (16, True, (1, 3)), (32, True, (2, 2))])
+def test_persistent_coarse_vcycle_vs_oracle(n, analytic, nu):
+    """csrc/coarse.cuh: the whole V-cycle below a grid size in one single-CTA kernel == the oracle's V-cycle."""
+    theta, ops, prm = _setup(n, analytic)
+    cfg = O.SubSolverConfig(kind="mg", cycles=1, nu1=nu[0], nu2=nu[1])
+    mg = O.Multigrid(ops, cfg)
+    last = mg.levels[-1]
+    rng = np.random.default_rng(7)
+    N = n * n
+    bF = rng.standard_normal(4 * N)
+    bP = rng.standard_normal(N)
+    bP -= bP.mean()
+    mm = 1 if analytic else 0
+    xF = emu.coarse_vcycle(True, n, prm, mm, theta, 4, 0.8, nu[0], nu[1], last.Finv, bF)
+    assert relerr(xF, mg._vcycle("F", 0, bF)) < 1e-11
+    xP = emu.coarse_vcycle(False, n, prm, mm, theta, 4, 0.8, nu[0], nu[1], last.Pinv, bP)
+    assert relerr(xP, mg._vcycle("P", 0, bP)) < 1e-11

@@ -1,5 +1,7 @@
 """Parity of the CUDA path (through the Python host -> C ABI -> kernels) against the CPU oracle and
 the golden fixtures generated from the reference's own code.  fp64; tolerances are stated per test."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -395,6 +397,33 @@ def test_fused_smoothing_kernels_vs_oracle(mp, monkeypatch, fuse, n, eta_n):
     v[4 * N:] -= v[4 * N:].mean()
     mg1 = O.Multigrid(ops, O.SubSolverConfig(kind="mg", cycles=1))
     assert relerr(p.call("mpbp_vcycle_F", v[:4 * N], 4 * N, 4 * N), mg1._vcycle("F", 0, v[:4 * N])) < 1e-10
+    Mo = O.ApproxSchur(ops, O.SubSolverConfig(kind="mg", cycles=3, cheb=True))
+    cfgP = O.SubSolverConfig(kind="mg", cycles=2, cheb=True)
+    Mo.P_inv = O.SubSolver(ops, "P", cfgP, O.Multigrid(ops, cfgP))
+    M = bp.approx_schur_operator(c, d)
+    assert relerr(M @ v, Mo.matvec(v)) < 1e-9
+
+
+@pytest.mark.skipif(os.environ.get("MPBP_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental persistent coarse V-cycle kernel (off by default); set MPBP_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("n,eta_n", [(64, 1e3), (128, 10.0)])
+def test_experimental_persistent_coarse_vcycle(mp, monkeypatch, n, eta_n):
+    """MPBP_COARSE=64: every level with n <= 64 runs inside one single-CTA kernel (csrc/coarse.cuh).
+    Logic-checked on the CPU shim (tests/test_emu_kernels.py); this is its GPU parity test."""
+    monkeypatch.setenv("MPBP_COARSE", "64")
+    xi, eta_s, c, d = 1.0, 1.0, 1.0, -1.0
+    sub = mp.SubSolver(kind="mg", F_cycles=3, P_cycles=2, cheb=True)
+    bp = mp.MultiphaseBlockPreconditioner(n, xi, eta_n, eta_s, sub_solver=sub)
+    p = bp.plan(c, d)
+    monkeypatch.delenv("MPBP_COARSE")
+    ops = O.Operators(n, xi, eta_n, eta_s, c, d)
+    rng = np.random.default_rng(5)
+    N = n * n
+    v = rng.standard_normal(5 * N)
+    v[4 * N:] -= v[4 * N:].mean()
+    mg1 = O.Multigrid(ops, O.SubSolverConfig(kind="mg", cycles=1))
+    assert relerr(p.call("mpbp_vcycle_F", v[:4 * N], 4 * N, 4 * N), mg1._vcycle("F", 0, v[:4 * N])) < 1e-10
+    assert relerr(p.call("mpbp_vcycle_P", v[4 * N:], N, N), mg1._vcycle("P", 0, v[4 * N:])) < 1e-10
     Mo = O.ApproxSchur(ops, O.SubSolverConfig(kind="mg", cycles=3, cheb=True))
     cfgP = O.SubSolverConfig(kind="mg", cycles=2, cheb=True)
     Mo.P_inv = O.SubSolver(ops, "P", cfgP, O.Multigrid(ops, cfgP))
