@@ -3,11 +3,11 @@
 // replacing ~9 launches per level.  On the small levels every kernel is pure launch latency (a few us each,
 // identical on 1 or 8 GPUs), so this is what the multi-GPU scaling and the replicated coarse levels need.
 //
-// EXPERIMENTAL in round 1 (off unless MPBP_COARSE=1): logic-checked against the oracle on the SIMT-on-CPU
-// shim (tests/emu), not yet measured on a B200.
+// EXPERIMENTAL in round 1 (off unless MPBP_COARSE=<n>): parity-tested on the B200 and on the SIMT-on-CPU shim
+// (tests/emu), not yet timed.
 //
 // The per-cell operator is written with the reference's coefficient table (preconditioner.py:127-179,
-// :242-295), independent of the flux form used by the marching kernels; it mirrors oracle/mpbp_oracle_c.c.
+// :242-295), independent of the flux form used by the marching kernels.
 #pragma once
 #include "stencil.cuh"
 

@@ -21,7 +21,10 @@ def load():
     if _lib is None:
         if not os.path.exists(OUT) or any(os.path.getmtime(s) > os.path.getmtime(OUT) for s in SRCS):
             os.makedirs(os.path.dirname(OUT), exist_ok=True)
-            cmd = ["g++", "-O1", "-std=c++17", "-pthread", "-fPIC", "-shared", "-ffp-contract=off", "-I" + HERE, "-o", OUT, SRCS[0]]
+            # -Bsymbolic: the kernel templates have the same mangled names as the CUDA launch stubs inside libmpbp.so
+            # (which other tests load RTLD_GLOBAL); this library must bind to its own host-compiled kernels
+            cmd = ["g++", "-O1", "-std=c++17", "-pthread", "-fPIC", "-shared", "-ffp-contract=off", "-Wl,-Bsymbolic",
+                   "-I" + HERE, "-o", OUT, SRCS[0]]
             res = subprocess.run(cmd, capture_output=True, text=True)
             if res.returncode != 0:
                 raise RuntimeError("g++ failed:\n" + res.stderr[-4000:])
