@@ -92,3 +92,13 @@ def coarse_vcycle(isF, n, prm, mass_mode, theta, n_coarse, omega, nu1, nu2, Minv
     load().emu_coarse_vcycle(int(isF), n, _p(prm), mass_mode, _p(th), n_coarse, C.c_double(omega), nu1, nu2, _p(Mt),
                              Minv.shape[0], _p(b), _p(x), threads)
     return x
+
+
+def slab_apply_A(P, rounds, n, prm, theta, x, rs=4):
+    """A.x with the grid split into P row slabs whose halo rows travel through the peer-memory push path
+    (k_halo_push -> comm buffer slots/flags -> in-kernel resolve), all "ranks" emulated in this process."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.zeros_like(x)
+    th = np.ascontiguousarray(theta, dtype=np.float64)
+    load().emu_slab_apply_A(P, rounds, n, _p(prm), _p(th), _p(x), _p(y), rs)
+    return y

@@ -168,4 +168,52 @@ void emu_coarse_vcycle(int isF, int n, const double* prm, int mass_mode, const d
   });
 }
 
+// P ranks of the slab decomposition emulated in ONE process: every "rank" owns a slab of x, a comm buffer with
+// the layout of plan.cu (flags + [slot][dir][5][n] halo areas) and a device-resident exchange counter.  First all
+// ranks run k_halo_push into their ring neighbours' buffers (so every flag is already set and nothing has to
+// spin), then every rank runs the consumer stencil kernel on its slab with the peer-pushed halo rows.  `rounds`
+// repeats push+apply to exercise the alternating slots.  y receives the assembled global result of A.x.
+void emu_slab_apply_A(int P, int rounds, int n, const double* prm, const double* theta, const double* x, double* y,
+                      int rs) {
+  const int rows = n / P;
+  const size_t fs = (size_t)rows * n, area = (size_t)5 * n;
+  const size_t comm_bytes = kFlagBytes + 4 * area * sizeof(double);
+  std::vector<std::vector<char>> comm(P, std::vector<char>(comm_bytes, 0));
+  std::vector<unsigned long long> dseq(P, 0ull);
+  std::vector<unsigned int> counter(P, 0u);
+  std::vector<std::vector<double>> xs(P, std::vector<double>(5 * fs)), ys(P, std::vector<double>(5 * fs)), thp(P);
+  std::vector<Tables> tabs(P);
+  for (int g = 0; g < P; ++g) {
+    for (int k = 0; k < 5; ++k)
+      std::memcpy(&xs[g][k * fs], x + (size_t)k * n * n + (size_t)g * rows * n, fs * sizeof(double));
+    thp[g].resize((size_t)(rows + 2) * n);
+    for (int r = -1; r <= rows; ++r)
+      std::memcpy(&thp[g][(size_t)(r + 1) * n], theta + (size_t)(((g * rows + r) % n + n) % n) * n, n * sizeof(double));
+  }
+  for (int it = 0; it < rounds; ++it) {
+    for (int g = 0; g < P; ++g) {
+      const int prev = (g + P - 1) % P, next = (g + 1) % P;
+      emu::launch(dim3((5 * n + 255) / 256), dim3(256), [&] {
+        k_halo_push(xs[g].data(), 5, fs, rows, n, comm[prev].data(), comm[next].data(), area, &dseq[g], &counter[g]);
+      });
+    }
+    for (int g = 0; g < P; ++g) {
+      const Phys ph = make_phys(n, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], prm[6], 1, tabs[g]);
+      const Geo geo{n, rows, g * rows, rs, 3};
+      VecIn in{};
+      in.x = xs[g].data();
+      in.fs = fs;
+      in.hs = n;
+      in.dseq = &dseq[g];
+      in.comm = comm[g].data();
+      in.area = area;
+      emu::launch(dim3((n + kWarpCols * kBlockWarps - 1) / (kWarpCols * kBlockWarps), (rows + rs - 1) / rs),
+                  dim3(kBlockThreads), [&] { k_stokes<0, true>(in, thp[g].data(), nullptr, ys[g].data(), geo, ph, 0.0); });
+    }
+  }
+  for (int g = 0; g < P; ++g)
+    for (int k = 0; k < 5; ++k)
+      std::memcpy(y + (size_t)k * n * n + (size_t)g * rows * n, &ys[g][k * fs], fs * sizeof(double));
+}
+
 }  // extern "C"

@@ -76,3 +76,15 @@ def test_persistent_coarse_vcycle_vs_oracle(n, analytic, nu):
     assert relerr(xF, mg._vcycle("F", 0, bF)) < 1e-11
     xP = emu.coarse_vcycle(False, n, prm, mm, theta, 4, 0.8, nu[0], nu[1], last.Pinv, bP)
     assert relerr(xP, mg._vcycle("P", 0, bP)) < 1e-11
+
+
+@pytest.mark.parametrize("P,rounds", [(2, 1), (2, 3), (4, 2)])
+def test_slab_halo_push_path_on_the_shim(P, rounds):
+    """The device side of the multi-GPU path (k_halo_push into the ring neighbours' comm buffers, alternating
+    slots keyed by the device-resident sequence number, in-kernel resolve of the halo pointers) with all ranks
+    emulated in one process: the assembled slab results equal the global A.x."""
+    n = 16
+    theta, ops, prm = _setup(n, True)
+    x = np.random.default_rng(P).standard_normal(5 * n * n)
+    got = emu.slab_apply_A(P, rounds, n, prm, theta, x, rs=3)
+    assert relerr(got, ops.A @ x) < 1e-13
