@@ -1739,6 +1739,7 @@ static int gmres_right(mpbp_plan* p, const double* b, double* x, const mpbp_gmre
 static int gmres_dispatch(mpbp_plan* p, const double* b, double* x, const mpbp_gmres_opts* o, double* hist,
                           int hist_cap, int* n_iters, int* info) {
   if (!o || o->restart < 1 || o->maxiter < 1) return set_err(MPBP_E_ARG, "gmres: bad options");
+  if (o->restart > kScal - 8) return set_err(MPBP_E_ARG, "gmres: restart must be <= %d", kScal - 8);
   size_t need = 0;
   RET(mpbp_gmres_workspace_bytes(p, o, &need));
   double* ws = nullptr;
