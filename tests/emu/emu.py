@@ -102,3 +102,26 @@ def slab_apply_A(P, rounds, n, prm, theta, x, rs=4):
     th = np.ascontiguousarray(theta, dtype=np.float64)
     load().emu_slab_apply_A(P, rounds, n, _p(prm), _p(th), _p(x), _p(y), rs)
     return y
+
+
+def div(n, prm, theta, w, add=None, scale=1.0, rs=4):
+    out = np.zeros(n * n)
+    thp = pad_theta(theta)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    add = None if add is None else np.ascontiguousarray(add, dtype=np.float64)
+    load().emu_div_grad(0, n, _p(prm), _p(thp), _p(w), _p(add), _p(out), rs, C.c_double(scale))
+    return out
+
+
+def grad(n, prm, theta, p, rs=4):
+    out = np.zeros(4 * n * n)
+    thp = pad_theta(theta)
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    load().emu_div_grad(1, n, _p(prm), _p(thp), _p(p), None, _p(out), rs, C.c_double(1.0))
+    return out
+
+
+def transfer(what, nf, x, out):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    load().emu_transfer(what, nf, _p(x), _p(out))
+    return out

@@ -97,6 +97,21 @@ void emu_poisson(int mode, int n, const double* prm, const double* th_pad, const
   });
 }
 
+void emu_div_grad(int what, int n, const double* prm, const double* th_pad, const double* in_, const double* add,
+                  double* out, int rs, double scale) {
+  // what 0: out = scale * D w + add (k_div) ; 1: out = G p (k_grad)
+  Tables t;
+  Phys ph = make_phys(n, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], prm[6], 0, t);
+  const Geo g{n, n, 0, rs, 0};
+  const VecIn in = whole_grid_view(in_, n);
+  if (what == 0) {
+    ph.inv_h *= scale;
+    emu::launch(sgrid(n, rs), dim3(kBlockThreads), [&] { k_div(in, th_pad, add, out, g, ph); });
+  } else {
+    emu::launch(sgrid(n, rs), dim3(kBlockThreads), [&] { k_grad(in, th_pad, out, (size_t)n * n, g, ph); });
+  }
+}
+
 void emu_transfer(int what, int nf, const double* in_, double* out) {
   // what: 0 restrict_F (in: fine 4 fields -> out: coarse), 1 prolong_add_F (in: coarse, out: fine, accumulates),
   //       2 restrict_P, 3 prolong_add_P

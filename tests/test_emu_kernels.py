@@ -88,3 +88,32 @@ def test_slab_halo_push_path_on_the_shim(P, rounds):
     x = np.random.default_rng(P).standard_normal(5 * n * n)
     got = emu.slab_apply_A(P, rounds, n, prm, theta, x, rs=3)
     assert relerr(got, ops.A @ x) < 1e-13
+
+
+def test_div_grad_transfer_and_fused_prolongation_kernels_on_the_shim():
+    n = 12
+    theta, ops, prm = _setup(n, False)
+    rng = np.random.default_rng(2)
+    N = n * n
+    w, pvec, add = rng.standard_normal(4 * N), rng.standard_normal(N), rng.standard_normal(N)
+    assert relerr(emu.div(n, prm, theta, w, add), ops.D @ w + add) < 1e-13
+    assert relerr(emu.div(n, prm, theta, w, None, scale=-1.0), -(ops.D @ w)) < 1e-13
+    assert relerr(emu.grad(n, prm, theta, pvec), ops.G @ pvec) < 1e-13
+    # transfers vs the oracle's restrict/prolong helpers
+    f4 = w.reshape(4, n, n)
+    ref_r = np.concatenate([O.restrict_u(f4[0]).ravel(), O.restrict_v(f4[1]).ravel(), O.restrict_u(f4[2]).ravel(),
+                            O.restrict_v(f4[3]).ravel()])
+    assert relerr(emu.transfer(0, n, w, np.zeros(N)), ref_r) < 1e-14
+    ec = rng.standard_normal(N)  # coarse 4 fields of (n/2)^2
+    e4 = ec.reshape(4, n // 2, n // 2)
+    ref_p = w + np.concatenate([O.prolong_u(e4[0]).ravel(), O.prolong_v(e4[1]).ravel(), O.prolong_u(e4[2]).ravel(),
+                                O.prolong_v(e4[3]).ravel()])
+    assert relerr(emu.transfer(1, n, ec, w.copy()), ref_p) < 1e-14
+    assert relerr(emu.transfer(2, n, pvec, np.zeros(N // 4)), O.restrict_cell(pvec.reshape(n, n)).ravel()) < 1e-14
+    assert relerr(emu.transfer(3, n, ec[:N // 4], pvec.copy()),
+                  pvec + O.prolong_cell(ec[:N // 4].reshape(n // 2, n // 2)).ravel()) < 1e-14
+    # fused prolongation + Jacobi sweep (k_stokes_fused<1>) == prolong_add followed by one damped sweep
+    b = rng.standard_normal(4 * N)
+    xt = ref_p
+    ref = xt + 0.8 * (b - ops.F @ xt) / ops.F.diagonal()
+    assert relerr(emu.stokes_fused(1, n, prm, 0, theta, w, b, ec=ec, rs=4), ref) < 1e-13
