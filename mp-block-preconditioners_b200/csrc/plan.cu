@@ -119,6 +119,10 @@ struct mpbp_plan {
   // bit 0: fused pre-smoothing pair (default: -10 % V-cycle time), bit 1: fused prolongation + first post-sweep
   // (128 registers, measured slower: off) -- whole-grid levels only, MPBP_FUSE overrides
   int fuse = 1;
+  // experimental (MPBP_PUSH_FUSED=1): smoothing / residual kernels on distributed levels push their own boundary
+  // rows to the neighbours; the next stencil kernel on that vector then skips its k_halo_push
+  bool push_fused = false;
+  const double* pending_push = nullptr;  // vector whose halo rows the last kernel already pushed
   int coarse_n = 0;  // experimental (MPBP_COARSE=<n>): whole-grid levels with n <= coarse_n run as ONE persistent kernel
   bool fused_mgs = true;
   int jac_minb = 0;  // __launch_bounds__ min blocks/SM variant of the Jacobi kernel (register cap)
@@ -256,10 +260,11 @@ static int choose_rs(int gx, int rows, int cap) {
 }
 static inline int ew_blocks(size_t len) { return (int)std::min<size_t>((len + 255) / 256, 148 * 16); }
 
-#define LAUNCH_CHECK(p)    \
-  do {                     \
-    (p)->launches++;       \
-    CU(cudaGetLastError()); \
+#define LAUNCH_CHECK(p)            \
+  do {                             \
+    (p)->launches++;               \
+    (p)->pending_push = nullptr;   \
+    CU(cudaGetLastError());        \
   } while (0)
 
 // neighbour rows of a distributed level's vector (nf fields, field stride fs) into lev.halo
@@ -295,7 +300,10 @@ static int make_view(mpbp_plan* p, Level& v, const double* x, int nf, VecIn& out
   out.x = x;
   out.fs = fs;
   if (v.dist) {
-    RET(halo_exchange(p, v, x, nf, fs));
+    // the kernel that produced x may already have pushed its boundary rows (fused push): nothing to exchange then
+    const bool already = p->p2p && p->pending_push != nullptr && p->pending_push == x;
+    if (!already) RET(halo_exchange(p, v, x, nf, fs));
+    p->pending_push = nullptr;
     if (p->p2p) {
       out.dseq = p->dseq;
       out.comm = p->comm_local;
@@ -330,7 +338,14 @@ static int op_stokes(mpbp_plan* p, int l, int mode, bool with_p, const double* x
     k_stokes<0, true><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega);
   else if (mode == 0)
     k_stokes<0, false><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega);
-  else if (mode == 1)
+  else if (v.dist && p->p2p && p->push_fused) {
+    const PushOut po{p->comm_prev, p->comm_next, p->comm_area, p->dseq, p->counter + 40};
+    if (mode == 1) k_stokes_push<1><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega, po);
+    else k_stokes_push<2><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega, po);
+    LAUNCH_CHECK(p);
+    p->pending_push = y;
+    return 0;
+  } else if (mode == 1)
     k_stokes<1, false><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega);
   else if (p->jac_minb == 6)
     k_stokes<2, false, 6><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega);
@@ -472,6 +487,7 @@ static int v_axpby(mpbp_plan* p, double a, const double* x, double b, const doub
   return 0;
 }
 static int v_copy(mpbp_plan* p, const double* x, double* y, size_t len) {
+  p->pending_push = nullptr;
   CU(cudaMemcpyAsync(y, x, len * sizeof(double), cudaMemcpyDeviceToDevice, p->st));
   return 0;
 }
@@ -1021,6 +1037,7 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
   if (const char* e = getenv("MPBP_FUSED_MGS")) p->fused_mgs = atoi(e) != 0;
   if (const char* e = getenv("MPBP_FUSE")) p->fuse = atoi(e);
   if (const char* e = getenv("MPBP_COARSE")) p->coarse_n = atoi(e);
+  if (const char* e = getenv("MPBP_PUSH_FUSED")) p->push_fused = atoi(e) != 0;
   if (cudaMemsetAsync(p->counter, 0, 64 * sizeof(unsigned int), nullptr) != cudaSuccess ||
       cudaMemsetAsync(p->dseq, 0, 16 * sizeof(unsigned long long), nullptr) != cudaSuccess)
     return fail(set_err(999, "memset failed"));

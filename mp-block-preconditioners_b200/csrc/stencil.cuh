@@ -209,16 +209,28 @@ __device__ __forceinline__ LaneGeom lane_geom(int n) {
   return g;
 }
 
+// Fused halo push (experimental, MPBP_PUSH_FUSED=1): the producing stencil kernel itself stores its first and
+// last output rows into the ring neighbours' comm buffers (peer memory over NVLink) and the last block of each
+// edge strip releases that direction's flag -- the compute kernel IS the halo exchange, and because the edge
+// strips are scheduled first the transfer overlaps the interior of the slab.
+struct PushOut {
+  char* prev_comm;            // neighbours' comm buffers (mapped peer memory)
+  char* next_comm;
+  size_t area;                // doubles per (slot, direction) halo area
+  unsigned long long* dseq;   // this rank's exchange counter: output rows go out under sequence *dseq + 1
+  unsigned int* counters;     // [0] first-strip blocks done, [1] last-strip blocks done, [2] all edge blocks done
+};
+
 // ------------------------------------------------------------------------------------------
 // Velocity-block / full-system kernel.
 //   MODE 0: y = Op x            (Op = F, or A when WITH_P)         K1 / K2
 //   MODE 1: y = b - F x                                             K2 residual
 //   MODE 2: y = x + omega * (b - F x) / diag(F)                     K3, solve.py:149-159 (damped)
 // ------------------------------------------------------------------------------------------
-template <int MODE, bool WITH_P, int MINB = 0>
-__global__ void __launch_bounds__(kBlockThreads, MINB) k_stokes(VecIn xin, const double* __restrict__ th,
-                                                          const double* __restrict__ b, double* __restrict__ y,
-                                                          Geo g, Phys ph, double omega) {
+template <int MODE, bool WITH_P, bool PUSH>
+__device__ __forceinline__ void stokes_body(VecIn xin, const double* __restrict__ th, const double* __restrict__ b,
+                                            double* __restrict__ y, const Geo& g, const Phys& ph, double omega,
+                                            const PushOut& po) {
   const LaneGeom lg = lane_geom(g.n);
   if (!lg.alive) return;
   const int n = g.n, rows = g.rows, c = lg.cc;
@@ -226,6 +238,15 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) k_stokes(VecIn xin, const
   const int r1 = min(r0 + g.rs, rows);
   if (r0 >= rows) return;
   halo_wait(xin, r0 == 0, r1 == rows);
+  unsigned long long seq_out = 0ull;
+  double* push_prev = nullptr;  // neighbour's bot area: receives my row 0
+  double* push_next = nullptr;  // neighbour's top area: receives my row rows-1
+  if (PUSH) {
+    seq_out = *po.dseq + 1ull;  // bumped only after every edge block of this launch has finished
+    const int slot = (int)(seq_out & 1ull);
+    push_prev = comm_halo(po.prev_comm, po.area, slot, 1);
+    push_next = comm_halo(po.next_comm, po.area, slot, 0);
+  }
 
   double sxf = 0.0, sxc = 0.0;
   if (ph.mass_mode) {
@@ -362,6 +383,20 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) k_stokes(VecIn xin, const
       y[off + 2 * fs] = y_us;
       y[off + 3 * fs] = y_vs;
       if (WITH_P && MODE == 0) y[off + 4 * fs] = y_p;
+      if (PUSH) {
+        if (r == 0) {
+          push_prev[c] = y_un;
+          push_prev[n + c] = y_vn;
+          push_prev[2 * n + c] = y_us;
+          push_prev[3 * n + c] = y_vs;
+        }
+        if (r == rows - 1) {
+          push_next[c] = y_un;
+          push_next[n + c] = y_vn;
+          push_next[2 * n + c] = y_us;
+          push_next[3 * n + c] = y_vs;
+        }
+      }
     }
     // rotate the window
     th_m = th_c; th_c = th_p; th_p = th_q;
@@ -372,6 +407,48 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) k_stokes(VecIn xin, const
     Tn_c = Tn_p; Ts_c = Ts_p; Qn_m = Qn_c; Qs_m = Qs_c;
     fv_c = fv_p; Vsum_c = Vsum_p;
   }
+  if (PUSH) {
+    const bool first = (r0 == 0), last = (r1 == rows);
+    if (first || last) {
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned int gx = gridDim.x;
+        const int slot = (int)(seq_out & 1ull);
+        if (first && atomicAdd(&po.counters[0], 1u) == gx - 1) {
+          po.counters[0] = 0u;
+          __threadfence_system();
+          st_release_sys(comm_flag(po.prev_comm, slot, 1), seq_out);
+        }
+        if (last && atomicAdd(&po.counters[1], 1u) == gx - 1) {
+          po.counters[1] = 0u;
+          __threadfence_system();
+          st_release_sys(comm_flag(po.next_comm, slot, 0), seq_out);
+        }
+        const unsigned int total = gx * ((gridDim.y == 1) ? 1u : 2u);
+        if (atomicAdd(&po.counters[2], 1u) == total - 1) {
+          po.counters[2] = 0u;
+          *po.dseq = seq_out;
+        }
+      }
+    }
+  }
+}
+
+template <int MODE, bool WITH_P, int MINB = 0>
+__global__ void __launch_bounds__(kBlockThreads, MINB) k_stokes(VecIn xin, const double* __restrict__ th,
+                                                          const double* __restrict__ b, double* __restrict__ y,
+                                                          Geo g, Phys ph, double omega) {
+  const PushOut po{};
+  stokes_body<MODE, WITH_P, false>(xin, th, b, y, g, ph, omega, po);
+}
+
+// same arithmetic, output rows 0 and rows-1 additionally pushed to the ring neighbours (see PushOut)
+template <int MODE>
+__global__ void __launch_bounds__(kBlockThreads) k_stokes_push(VecIn xin, const double* __restrict__ th,
+                                                               const double* __restrict__ b, double* __restrict__ y,
+                                                               Geo g, Phys ph, double omega, PushOut po) {
+  stokes_body<MODE, false, true>(xin, th, b, y, g, ph, omega, po);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -125,3 +125,12 @@ def transfer(what, nf, x, out):
     x = np.ascontiguousarray(x, dtype=np.float64)
     load().emu_transfer(what, nf, _p(x), _p(out))
     return out
+
+
+def slab_fused_push_chain(P, n, prm, theta, x0, b, rs=4, omega=0.8):
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    out = np.zeros_like(b)
+    th = np.ascontiguousarray(theta, dtype=np.float64)
+    load().emu_slab_fused_push_chain(P, n, _p(prm), _p(th), _p(x0), _p(b), _p(out), rs, C.c_double(omega))
+    return out

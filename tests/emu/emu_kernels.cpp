@@ -231,4 +231,66 @@ void emu_slab_apply_A(int P, int rounds, int n, const double* prm, const double*
       std::memcpy(y + (size_t)k * n * n + (size_t)g * rows * n, &ys[g][k * fs], fs * sizeof(double));
 }
 
+// Fused halo push chain on P emulated ranks: x0 --k_halo_push--> sweep (fused push) -> sweep (fused push) ->
+// residual.  Every kernel is run for all ranks before the next one starts, so all flags are set when read.
+// out receives the assembled global residual b - F x2 with x_{k+1} = x_k + omega (b - F x_k)/diag.
+void emu_slab_fused_push_chain(int P, int n, const double* prm, const double* theta, const double* x0, const double* b,
+                               double* out, int rs, double omega) {
+  const int rows = n / P;
+  const size_t fs = (size_t)rows * n, area = (size_t)5 * n;
+  const size_t comm_bytes = kFlagBytes + 4 * area * sizeof(double);
+  std::vector<std::vector<char>> comm(P, std::vector<char>(comm_bytes, 0));
+  std::vector<unsigned long long> dseq(P, 0ull);
+  std::vector<std::vector<unsigned int>> counter(P, std::vector<unsigned int>(8, 0u));
+  std::vector<std::vector<double>> xa(P, std::vector<double>(4 * fs)), xb(P, std::vector<double>(4 * fs)),
+      bs(P, std::vector<double>(4 * fs)), thp(P);
+  std::vector<Tables> tabs(P);
+  for (int g = 0; g < P; ++g) {
+    for (int k = 0; k < 4; ++k) {
+      std::memcpy(&xa[g][k * fs], x0 + (size_t)k * n * n + (size_t)g * rows * n, fs * sizeof(double));
+      std::memcpy(&bs[g][k * fs], b + (size_t)k * n * n + (size_t)g * rows * n, fs * sizeof(double));
+    }
+    thp[g].resize((size_t)(rows + 2) * n);
+    for (int r = -1; r <= rows; ++r)
+      std::memcpy(&thp[g][(size_t)(r + 1) * n], theta + (size_t)(((g * rows + r) % n + n) % n) * n, n * sizeof(double));
+  }
+  const dim3 grid((n + kWarpCols * kBlockWarps - 1) / (kWarpCols * kBlockWarps), (rows + rs - 1) / rs);
+  auto view = [&](int g, const double* x) {
+    VecIn in{};
+    in.x = x;
+    in.fs = fs;
+    in.hs = n;
+    in.dseq = &dseq[g];
+    in.comm = comm[g].data();
+    in.area = area;
+    return in;
+  };
+  // exchange 1: classic push kernel of x0
+  for (int g = 0; g < P; ++g) {
+    const int prev = (g + P - 1) % P, next = (g + 1) % P;
+    emu::launch(dim3((4 * n + 255) / 256), dim3(256), [&] {
+      k_halo_push(xa[g].data(), 4, fs, rows, n, comm[prev].data(), comm[next].data(), area, &dseq[g], &counter[g][0]);
+    });
+  }
+  // two sweeps with fused pushes (ping-pong xa -> xb -> xa), then the residual of xa into xb
+  for (int step = 0; step < 3; ++step) {
+    for (int g = 0; g < P; ++g) {
+      const int prev = (g + P - 1) % P, next = (g + 1) % P;
+      const Phys ph = make_phys(n, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], prm[6], 1, tabs[g]);
+      const Geo geo{n, rows, g * rows, rs, 3};
+      const double* src = (step == 1) ? xb[g].data() : xa[g].data();
+      double* dst = (step == 1) ? xa[g].data() : xb[g].data();
+      const VecIn in = view(g, src);
+      const PushOut po{comm[prev].data(), comm[next].data(), area, &dseq[g], &counter[g][4]};
+      emu::launch(grid, dim3(kBlockThreads), [&] {
+        if (step < 2) k_stokes_push<2>(in, thp[g].data(), bs[g].data(), dst, geo, ph, omega, po);
+        else k_stokes<1, false>(in, thp[g].data(), bs[g].data(), dst, geo, ph, omega);
+      });
+    }
+  }
+  for (int g = 0; g < P; ++g)
+    for (int k = 0; k < 4; ++k)
+      std::memcpy(out + (size_t)k * n * n + (size_t)g * rows * n, &xb[g][k * fs], fs * sizeof(double));
+}
+
 }  // extern "C"

@@ -117,3 +117,19 @@ def test_div_grad_transfer_and_fused_prolongation_kernels_on_the_shim():
     xt = ref_p
     ref = xt + 0.8 * (b - ops.F @ xt) / ops.F.diagonal()
     assert relerr(emu.stokes_fused(1, n, prm, 0, theta, w, b, ec=ec, rs=4), ref) < 1e-13
+
+
+@pytest.mark.parametrize("P,rs", [(2, 3), (2, 8), (4, 2), (4, 4)])
+def test_fused_halo_push_chain_on_the_shim(P, rs):
+    """Experimental fused push (k_stokes_push): two Jacobi sweeps that push their own boundary rows to the ring
+    neighbours, followed by a residual that consumes them -- no k_halo_push launch after the first exchange.
+    rs=8 makes one strip per 8-row slab (a block that is both the first and the last strip)."""
+    n = 16
+    theta, ops, prm = _setup(n, True)
+    rng = np.random.default_rng(P + rs)
+    x0, b = rng.standard_normal(4 * n * n), rng.standard_normal(4 * n * n)
+    dg = ops.F.diagonal()
+    x1 = x0 + 0.8 * (b - ops.F @ x0) / dg
+    x2 = x1 + 0.8 * (b - ops.F @ x1) / dg
+    got = emu.slab_fused_push_chain(P, n, prm, theta, x0, b, rs=rs)
+    assert relerr(got, b - ops.F @ x2) < 1e-12
