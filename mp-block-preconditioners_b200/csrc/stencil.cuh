@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) k_stokes(VecIn xin, const
 
 // same arithmetic, output rows 0 and rows-1 additionally pushed to the ring neighbours (see PushOut)
 template <int MODE>
-__global__ void __launch_bounds__(kBlockThreads) k_stokes_push(VecIn xin, const double* __restrict__ th,
+__global__ void __launch_bounds__(kBlockThreads, 5) k_stokes_push(VecIn xin, const double* __restrict__ th,
                                                                const double* __restrict__ b, double* __restrict__ y,
                                                                Geo g, Phys ph, double omega, PushOut po) {
   stokes_body<MODE, false, true>(xin, th, b, y, g, ph, omega, po);
