@@ -1,5 +1,6 @@
 #!/bin/bash
 # usage: run_multi_gpu.sh N [check]  -- bounded multi-GPU run: optional parity check at n=2048, then the bench
+# experimental paths are selected through the environment, e.g.  MPBP_PUSH_FUSED=1 MPBP_COARSE=64 run_multi_gpu.sh 2 check
 N=$1
 if [ "$2" = "check" ]; then
 timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 tests/mgpu_check.py 2048 > gpurun_out/mgpu${N}b.log 2>&1
