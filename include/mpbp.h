@@ -78,6 +78,8 @@ int mpbp_plan_workspace_bytes(const mpbp_config* cfg, size_t* bytes);
 int mpbp_plan_create(mpbp_plan** plan, const mpbp_config* cfg);
 int mpbp_plan_destroy(mpbp_plan* plan);
 const char* mpbp_last_error_string(void);
+/* hash of the sources the loaded binary was compiled from (the host side refuses a binary that does not match the tree) */
+const char* mpbp_build_id(void);
 int mpbp_nccl_unique_id(void* out128);
 /* queries */
 int mpbp_plan_rows_local(const mpbp_plan* plan); /* rows of the slab owned by this rank */

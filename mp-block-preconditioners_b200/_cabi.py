@@ -67,6 +67,7 @@ SIGNATURES = {
     "mpbp_plan_create": (C.c_int, [C.POINTER(_P), C.POINTER(Config)]),
     "mpbp_plan_destroy": (C.c_int, [_P]),
     "mpbp_last_error_string": (C.c_char_p, []),
+    "mpbp_build_id": (C.c_char_p, []),
     "mpbp_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "mpbp_plan_rows_local": (C.c_int, [_P]),
     "mpbp_plan_num_levels": (C.c_int, [_P]),
@@ -113,11 +114,22 @@ def load():
         raise ImportError(
             f"{LIB_PATH} not found: the CUDA extension is not built (run `python -c 'import __graft_entry__ as g; "
             "g.build()'`). This package has no CPU fallback.")
+    from . import _build
+    if _build.binary_id(LIB_PATH) != _build.source_id():
+        # stale binary (sources edited after the last build): rebuild when a compiler is here, never run it silently
+        try:
+            _build.build(force=True)
+        except Exception as exc:
+            raise ImportError(f"{LIB_PATH} was built from different sources than the tree (build id "
+                              f"{_build.binary_id(LIB_PATH)} != {_build.source_id()}) and cannot be rebuilt: {exc}")
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    bid = lib.mpbp_build_id().decode()
+    if bid != _build.source_id():
+        raise ImportError(f"libmpbp.so build id {bid} does not match the source tree {_build.source_id()}")
     _lib = lib
     return lib
 

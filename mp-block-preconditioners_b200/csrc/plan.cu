@@ -872,6 +872,9 @@ extern "C" int mpbp_plan_workspace_bytes(const mpbp_config* cfg, size_t* bytes) 
 
 // dense inverse by Gauss-Jordan with partial pivoting (row-major, in place); returns false if singular
 static bool invert_dense(std::vector<double>& A, int m) {
+  double amax = 0.0;
+  for (double v : A) amax = std::max(amax, std::fabs(v));
+  const double tiny = 1e-13 * amax;  // relative pivot threshold: a numerically singular coarse operator is an error
   std::vector<double> I((size_t)m * m, 0.0);
   for (int i = 0; i < m; ++i) I[(size_t)i * m + i] = 1.0;
   for (int col = 0; col < m; ++col) {
@@ -881,7 +884,7 @@ static bool invert_dense(std::vector<double>& A, int m) {
       const double v = std::fabs(A[(size_t)r * m + col]);
       if (v > best) best = v, piv = r;
     }
-    if (best == 0.0) return false;
+    if (!(best > tiny)) return false;
     if (piv != col)
       for (int k = 0; k < m; ++k) {
         std::swap(A[(size_t)piv * m + k], A[(size_t)col * m + k]);
@@ -1118,8 +1121,9 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
       v.geo.rows = v.rows;
       v.geo.row0 = v.row0;
       const int gx = (n + kWarpCols * kBlockWarps - 1) / (kWarpCols * kBlockWarps);
-      int sms_ = 148;
-      cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, 0);
+      int sms_ = 148, dev_ = 0;
+      cudaGetDevice(&dev_);
+      cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, dev_);
       v.geo.rs = choose_rs(gx, v.rows, 5 * sms_);
       v.geo.pf = 3;  // measured best on B200 at 4096^2 (profiles/r1_tuning.txt)
       if (const char* e = getenv("MPBP_PF")) v.geo.pf = std::max(0, std::min(atoi(e), 64));
@@ -1188,6 +1192,13 @@ extern "C" int mpbp_plan_destroy(mpbp_plan* p) {
 }
 
 extern "C" const char* mpbp_last_error_string(void) { return g_err; }
+
+#ifndef MPBP_BUILD_ID_STR
+#define MPBP_BUILD_ID_STR "unknown"
+#endif
+// hash of the sources this binary was compiled from (written by _build.py); the marker makes it greppable in the file
+static const char g_build_id[] = "MPBP_BUILD_ID=" MPBP_BUILD_ID_STR;
+extern "C" const char* mpbp_build_id(void) { return g_build_id + 14; }
 
 extern "C" int mpbp_nccl_unique_id(void* out128) {
   if (!out128) return set_err(MPBP_E_ARG, "null output");

@@ -93,7 +93,12 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 #endif
-// warp-level wait for the neighbours' halo rows (called by whole warps; lane 0 polls)
+// warp-level wait for the neighbours' halo rows (called by whole warps; lane 0 polls).
+// Slot-reuse invariant (two slots, sequence s lives in slot s&1): a rank's push s+2 overwrites the slot its
+// neighbours read for sequence s, so it must be ordered after BOTH neighbours' consumers of sequence s.  That
+// holds only if every consumer kernel of sequence s+1 on this rank acquires BOTH neighbours' flags (each
+// neighbour's push s+1 is stream-ordered after its own consumer of s).  Hence every halo consumer calls this
+// with need_top on its first strip and need_bot on its last strip, even when it reads one side only.
 __device__ __forceinline__ void halo_wait(VecIn& v, bool need_top, bool need_bot) {
   if (v.dseq == nullptr) return;
   resolve_halo(v);
@@ -736,7 +741,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_div(VecIn win, const double* 
   const int r0 = blockIdx.y * g.rs;
   const int r1 = min(r0 + g.rs, rows);
   if (r0 >= rows) return;
-  halo_wait(win, false, r1 == rows);
+  halo_wait(win, r0 == 0, r1 == rows);  // both flags: see halo_wait (slot reuse needs a two-sided acquire)
   double th_m = th_row(th, r0 - 1, n)[c];
   double th_c = th_row(th, r0, n)[c];
   double vn_c = row_ptr(win, 1, r0, rows, n)[c], vs_c = row_ptr(win, 3, r0, rows, n)[c];
@@ -768,7 +773,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_grad(VecIn pin, const double*
   const int r0 = blockIdx.y * g.rs;
   const int r1 = min(r0 + g.rs, rows);
   if (r0 >= rows) return;
-  halo_wait(pin, r0 == 0, false);
+  halo_wait(pin, r0 == 0, r1 == rows);
   double th_m = th_row(th, r0 - 1, n)[c];
   double p_m = row_ptr(pin, 0, r0 - 1, rows, n)[c];
 #pragma unroll 2
@@ -798,7 +803,7 @@ __global__ void k_restrict_F(VecIn fin, double* __restrict__ yc, int nf, int row
   const int nc = nf >> 1, rows_c = rows_f >> 1;
   const int C = blockIdx.x * blockDim.x + threadIdx.x;
   const int R = blockIdx.y;
-  halo_wait(fin, R == 0, false);
+  halo_wait(fin, R == 0, R == (rows_f >> 1) - 1);
   if (C >= nc || R >= rows_c) return;
   const size_t fsc = (size_t)rows_c * nc;
   const int c0 = 2 * C, cm = (c0 == 0) ? nf - 1 : c0 - 1, cp = c0 + 1;
@@ -822,7 +827,7 @@ __global__ void k_prolong_add_F(VecIn cin, double* __restrict__ xf, int nf, int 
   const int nc = nf >> 1, rows_c = rows_f >> 1;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;
-  halo_wait(cin, false, r == rows_f - 1);
+  halo_wait(cin, r == 0, r == rows_f - 1);
   if (c >= nf || r >= rows_f) return;
   const size_t fsf = (size_t)rows_f * nf;
   const int C = c >> 1, R = r >> 1;
