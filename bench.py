@@ -92,52 +92,68 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (numpy/scipy) on a bounded sample of the workload
 # ----------------------------------------------------------------------------------------------
-def cpu_port_its_per_s(steps, warmup, n_sample=1024):
-    """Times `steps` FGMRES iterations of the CPU oracle port on an n_sample^2 grid (same contrast, same
-    sub-solver definition and restart) and scales its/s to the 4096^2 workload by the cell ratio.
-    The port is the OpenMP C restatement (oracle/mpbp_oracle_c.c) on all host threads; if it cannot be
-    built, the numpy/scipy oracle (single-threaded CSR mat-vecs) is timed instead and labelled so."""
+def _host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def _host_free_gb():
+    try:
+        import psutil
+        return psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        return 0.0
+
+
+def cpu_port_its_per_s(steps, warmup, n_sample=None):
+    """Times `steps` FGMRES iterations of the CPU oracle port (same contrast, same sub-solver definition and
+    restart) on the host cores.  The sample is the REAL 4096^2 workload whenever the host has the memory for it
+    (about 20 GB: hierarchy + the few Krylov bases the bounded sample touches); only otherwise a smaller grid whose
+    its/s is scaled by the cell ratio -- the line says which.  The port is the OpenMP C restatement
+    (oracle/mpbp_oracle_c.c) on every core this process may use (torchrun's OMP_NUM_THREADS=1 is overridden)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import mpbp_oracle as O
     w = WORKLOAD
+    if n_sample is None:
+        free = _host_free_gb()
+        n_sample = w["n"] if free >= 40 else (2048 if free >= 12 else 1024)
     scale = (n_sample / w["n"]) ** 2
     _, b = O.manufactured(n_sample, w["c"], w["d_u"], w["xi"], w["eta_n"], w["eta_s"])
-    try:
-        from c_oracle import COracle
-        co = COracle(n_sample, w["xi"], w["eta_n"], w["eta_s"], w["c"], w["d_u"], kind="mg", F_cycles=SUB["F_cycles"],
-                     P_cycles=SUB["P_cycles"], cheb=True, omega=SUB["omega"], nu1=SUB["nu1"], nu2=SUB["nu2"],
-                     n_coarse=SUB["n_coarse"])
-        if warmup > 0:
-            co.fgmres(b, tol=0.0, restart=w["restart"], maxiter=1)
-        t0 = time.perf_counter()
-        _, _, hist = co.fgmres(b, tol=0.0, restart=w["restart"], maxiter=steps)
-        dt = time.perf_counter() - t0
-        its, threads, what = len(hist), co.threads, "OpenMP C oracle (oracle/mpbp_oracle_c.c)"
-    except Exception as exc:  # no compiler on the box: fall back to the numpy oracle
-        ops = O.Operators(n_sample, w["xi"], w["eta_n"], w["eta_s"], w["c"], w["d_u"])
-        cfgF = O.SubSolverConfig(kind="mg", cycles=SUB["F_cycles"], cheb=True)
-        cfgP = O.SubSolverConfig(kind="mg", cycles=SUB["P_cycles"], cheb=True)
-        M = O.ApproxSchur(ops, cfgF)
-        M.P_inv = O.SubSolver(ops, "P", cfgP, O.Multigrid(ops, cfgP))
-        t0 = time.perf_counter()
-        O.fgmres(ops.A, b, M=M.linear_operator(), tol=0.0, maxiter=steps, restart=w["restart"])
-        dt = time.perf_counter() - t0
-        its, threads, what = len(O.fgmres.last_history), 1, f"numpy/scipy oracle (C oracle unavailable: {exc})"
-    return dict(value=its / dt * scale, unit=UNIT, cores=threads, kind="port",
-                sample=f"{its} FGMRES iterations of the {what} on a {n_sample}^2 grid ({dt:.1f} s on {threads} host "
-                       f"threads; host has {os.cpu_count()} cores), its/s scaled by the cell ratio {scale:.5f} to 4096^2",
-                ms_per_step=dt / its / scale * 1e3)
+    from c_oracle import COracle, set_threads
+    threads = set_threads(_host_threads())
+    co = COracle(n_sample, w["xi"], w["eta_n"], w["eta_s"], w["c"], w["d_u"], kind="mg", F_cycles=SUB["F_cycles"],
+                 P_cycles=SUB["P_cycles"], cheb=True, omega=SUB["omega"], nu1=SUB["nu1"], nu2=SUB["nu2"],
+                 n_coarse=SUB["n_coarse"], lmin=SUB.get("lmin", 0.75), lmax=SUB.get("lmax", 1.2))
+    if warmup > 0:
+        co.fgmres(b, tol=0.0, restart=w["restart"], maxiter=1)
+    t0 = time.perf_counter()
+    _, _, hist = co.fgmres(b, tol=0.0, restart=w["restart"], maxiter=steps)
+    dt = time.perf_counter() - t0
+    its = len(hist)
+    what = "OpenMP C oracle (oracle/mpbp_oracle_c.c)"
+    if n_sample == w["n"]:
+        sample = (f"{its} FGMRES iterations (Arnoldi bases 1..{its}) of the {what} on the full {n_sample}^2 workload, "
+                  f"{dt:.1f} s on {threads} host threads (host has {os.cpu_count()} cores); measured, not extrapolated")
+    else:
+        sample = (f"{its} FGMRES iterations of the {what} on a {n_sample}^2 grid ({dt:.1f} s on {threads} host threads; "
+                  f"host has {os.cpu_count()} cores, {_host_free_gb():.0f} GB free: too little for 4096^2), its/s scaled "
+                  f"by the cell ratio {scale:.5f} to 4096^2 (EXTRAPOLATED)")
+    return dict(value=its / dt * scale, unit=UNIT, cores=threads, kind="port", sample=sample, steps=its, seconds=dt,
+                ms_per_step=dt / its / scale * 1e3, n_sample=n_sample)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = min(args.steps, 12)
+    steps = max(1, min(args.steps, 3))  # a bounded sample: ~7 s per iteration at 4096^2 on 16 cores
     res = cpu_port_its_per_s(steps, min(args.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "steps": res["steps"], "steps_requested": args.steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args.gpus), "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -268,6 +284,9 @@ def run_gpu(args):
     }
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- in-run parity check (outside every timed region): the record carries its own evidence ----
+    parity = run_parity(mp, p, A, M, b_dev, z, n, w, sub, rank, world) if not args.no_parity else None
+
     # ---- end to end through the public Python API with HOST buffers: one FGMRES cycle per call ----
     del xF, z
     e2e_calls = max(1, min(2, args.steps // restart))
@@ -296,12 +315,13 @@ def run_gpu(args):
                    f"copied D2H inside every call ({5 * N * 8 * world} bytes each way per call)"}
 
     if rank == 0:
-        cpu = cpu_port_its_per_s(8, 1) if (world == 1 and not args.no_cpu) else None
+        cpu = cpu_port_its_per_s(2, 1) if (world == 1 and not args.no_cpu) else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config_dict(world) if not args.n else {**config_dict(world), "n": n, "workload": f"override n={n}"},
-                "roofline": roof, "kernels": kernels, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
+                "roofline": roof, "kernels": kernels, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "parity": parity}
         if cpu:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         _emit(line)
@@ -313,6 +333,66 @@ def run_gpu(args):
         dist.barrier()
         torch.cuda.synchronize()
         os._exit(0)
+
+
+def run_parity(mp, p, A, M, b_dev, z, n, w, sub, rank, world):
+    """Parity evidence carried by every bench line (never timed).
+    N = 1: the GPU's approx_schur_op (solve.py:257-277) and A.x against the C oracle on a 1024^2 grid with the
+           benchmarked contrast and sub-solver (the oracle finishes there in about a second);
+    N > 1: the slab-distributed apply and A.x of the BENCHMARKED workload against a single-GPU plan of the same grid
+           evaluated on the same global vector, max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    def rel(a, b):
+        return float((a - b).abs().max() / b.abs().max())
+    if world == 1:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        from c_oracle import COracle, set_threads
+        import mpbp_oracle as O
+        m = 1024
+        set_threads(_host_threads())
+        co = COracle(m, w["xi"], w["eta_n"], w["eta_s"], w["c"], w["d_u"],
+                     **{k: v for k, v in SUB.items()})
+        bp = mp.MultiphaseBlockPreconditioner(m, w["xi"], w["eta_n"], w["eta_s"], sub_solver=sub)
+        Am = bp.get_big_A_matrix(c=w["c"], d_u=w["d_u"])[0]
+        Mm = bp.approx_schur_operator(c=w["c"], d_u=w["d_u"])
+        rng = np.random.default_rng(1024)
+        v = rng.standard_normal(5 * m * m)
+        v[4 * m * m:] -= v[4 * m * m:].mean()
+        _, b = O.manufactured(m, w["c"], w["d_u"], w["xi"], w["eta_n"], w["eta_s"])
+
+        def nrel(a, b_):
+            return float(np.abs(a - b_).max() / np.abs(b_).max())
+        out = {"against": "C oracle (oracle/mpbp_oracle_c.c), 1024^2, benchmarked contrast and sub-solver",
+               "apply_A_relerr": nrel(Am @ v, co.apply_A(v)),
+               "precond_apply_relerr": nrel(Mm @ v, co.precond(v)),
+               "precond_apply_rhs_relerr": nrel(Mm @ b, co.precond(b)),
+               "tolerance": {"apply_A": 1e-13, "precond_apply": 1e-9}}
+        out["ok"] = bool(out["apply_A_relerr"] < 1e-13 and out["precond_apply_relerr"] < 1e-9
+                         and out["precond_apply_rhs_relerr"] < 1e-9)
+        Am.plan.close()
+        return out
+    from mp_block_preconditioners_b200.parallel import scatter_slab
+    from mp_block_preconditioners_b200.utils import manufactured_device
+    bp1 = mp.MultiphaseBlockPreconditioner(n, w["xi"], w["eta_n"], w["eta_s"], sub_solver=sub)
+    A1 = bp1.get_big_A_matrix(c=w["c"], d_u=w["d_u"])[0]
+    M1 = bp1.approx_schur_operator(c=w["c"], d_u=w["d_u"])
+    _, b1 = manufactured_device(A1.plan)
+    e_b = rel(b_dev, scatter_slab(b1, n, 5, rank, world))
+    z1 = M1 @ b1
+    e_M = rel(M @ b_dev, scatter_slab(z1, n, 5, rank, world))
+    e_A = rel(A @ b_dev, scatter_slab(A1 @ b1, n, 5, rank, world))
+    del z1, b1
+    A1.plan.close()
+    torch.cuda.empty_cache()
+    t = torch.tensor([e_b, e_A, e_M], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e_b, e_A, e_M = (float(v) for v in t)
+    return {"against": f"single-GPU plan of the same {n}^2 workload on the same global vector (max over {world} ranks)",
+            "rhs_relerr": e_b, "apply_A_relerr": e_A, "precond_apply_relerr": e_M,
+            "tolerance": {"apply_A": 1e-13, "precond_apply": 1e-9}, "ok": bool(e_A < 1e-13 and e_M < 1e-9)}
 
 
 _REAL_STDOUT = None
@@ -344,6 +424,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=0, help="override the grid size (debugging only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity block")
     args = ap.parse_args()
     _capture_stdout()
     if args.impl == "reference":

@@ -38,6 +38,8 @@ def load():
                                  [C.c_double] * 2 + [C.c_int]
         lib.oc_destroy.argtypes = [C.c_void_p]
         lib.oc_num_threads.restype = C.c_int
+        lib.oc_set_num_threads.argtypes = [C.c_int]
+        lib.oc_set_noise.argtypes = [C.c_double, C.c_ulonglong]
         for name in ("oc_apply_A", "oc_apply_F", "oc_apply_G", "oc_apply_D", "oc_apply_GtG", "oc_precond"):
             getattr(lib, name).argtypes = [C.c_void_p, _dp, _dp]
         lib.oc_vcycle.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
@@ -46,6 +48,18 @@ def load():
         lib.oc_fgmres.argtypes = [C.c_void_p, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_int, _dp, C.POINTER(C.c_int)]
         _lib = lib
     return _lib
+
+
+def set_threads(t=None):
+    """Use `t` OpenMP threads (default: every core this process may run on, whatever OMP_NUM_THREADS says)."""
+    t = int(t) if t else len(os.sched_getaffinity(0))
+    load().oc_set_num_threads(t)
+    return load().oc_num_threads()
+
+
+def set_noise(amp=0.0, seed=0):
+    """Conditioning probe: ~amp relative noise on b and on every A.x / M.v inside COracle.fgmres (0 = off)."""
+    load().oc_set_noise(float(amp), int(seed))
 
 
 def _p(a):

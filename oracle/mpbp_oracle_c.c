@@ -542,6 +542,15 @@ int oc_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the baseline legs set the thread count explicitly */
+void oc_set_num_threads(int t) {
+#ifdef _OPENMP
+  if (t > 0) omp_set_num_threads(t);
+#else
+  (void)t;
+#endif
+}
+
 void oc_apply_A(oc_ctx* C, const double* x, double* y) { stokes_op(C, &C->lev[0], 0, 1, x, NULL, y, 0.0); }
 void oc_apply_F(oc_ctx* C, const double* x, double* y) { stokes_op(C, &C->lev[0], 0, 0, x, NULL, y, 0.0); }
 void oc_apply_G(oc_ctx* C, const double* p, double* y) { grad_op(C, &C->lev[0], p, y); }
@@ -566,18 +575,47 @@ void oc_precond(oc_ctx* C, const double* v, double* z) {
 }
 
 /* right-preconditioned flexible GMRES (call shape of pyamg.krylov.fgmres at solve.py:285); returns iterations */
-int oc_fgmres(oc_ctx* C, const double* b, double* x, double tol, int restart, int maxiter, int use_pc, double* hist,
+/* Conditioning probe for the residual-history tests: when amp > 0, the result of every A.x and M.v inside
+ * oc_fgmres (and b itself) is multiplied elementwise by (1 + amp*u), u ~ U(-sqrt3, sqrt3) (unit variance), a
+ * deterministic hash of (seed, call, index).  amp = 1.2e-16 models "another correct fp64 implementation". */
+static double g_noise_amp = 0.0;
+static unsigned long long g_noise_seed = 0, g_noise_call = 0;
+void oc_set_noise(double amp, unsigned long long seed) { g_noise_amp = amp; g_noise_seed = seed; g_noise_call = 0; }
+static void add_noise(double* y, size_t len) {
+  if (g_noise_amp <= 0.0) return;
+  const unsigned long long base = (g_noise_seed * 0x9E3779B97F4A7C15ull) ^ ((++g_noise_call) * 0xBF58476D1CE4E5B9ull);
+#pragma omp parallel for schedule(static)
+  for (size_t i = 0; i < len; ++i) {
+    unsigned long long z = base + (unsigned long long)i * 0x94D049BB133111EBull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const double u = ((double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5) * 3.4641016151377544;
+    y[i] *= 1.0 + g_noise_amp * u;
+  }
+}
+
+int oc_fgmres(oc_ctx* C, const double* b_in, double* x, double tol, int restart, int maxiter, int use_pc, double* hist,
               int* info) {
   const size_t len = 5 * (size_t)C->lev[0].n * C->lev[0].n;
   const int m = restart;
-  double* V = (double*)malloc((size_t)(m + 1) * len * sizeof(double));
-  double* Z = (double*)malloc((size_t)m * len * sizeof(double));
+  const int mb = m < maxiter ? m : maxiter; /* bases actually touched (a bounded sample never needs all m) */
+  double* V = (double*)malloc((size_t)(mb + 1) * len * sizeof(double));
+  double* Z = (double*)malloc((size_t)mb * len * sizeof(double));
   double* w = (double*)malloc(len * sizeof(double));
   double* H = (double*)calloc((size_t)(m + 1) * m, sizeof(double));
   double* cs = (double*)calloc(m, sizeof(double));
   double* sn = (double*)calloc(m, sizeof(double));
   double* g = (double*)calloc(m + 1, sizeof(double));
   double* yv = (double*)calloc(m, sizeof(double));
+  double* bcopy = NULL;
+  const double* b = b_in;
+  if (g_noise_amp > 0.0) {
+    bcopy = (double*)malloc(len * sizeof(double));
+    memcpy(bcopy, b_in, len * sizeof(double));
+    add_noise(bcopy, len);
+    b = bcopy;
+  }
   double bn = sqrt(vdot(b, b, len));
   if (bn == 0.0) bn = 1.0;
   memset(x, 0, len * sizeof(double));
@@ -595,8 +633,9 @@ int oc_fgmres(oc_ctx* C, const double* b, double* x, double tol, int restart, in
     double res = beta;
     for (int j = 0; j < m; ++j) {
       double* zj = Z + (size_t)j * len;
-      if (use_pc) oc_precond(C, V + (size_t)j * len, zj); else vcopy(V + (size_t)j * len, zj, len);
+      if (use_pc) { oc_precond(C, V + (size_t)j * len, zj); add_noise(zj, len); } else vcopy(V + (size_t)j * len, zj, len);
       oc_apply_A(C, zj, w);
+      add_noise(w, len);
       for (int i = 0; i <= j; ++i) {
         const double hij = vdot(V + (size_t)i * len, w, len);
         H[(size_t)i * m + j] = hij;
@@ -631,6 +670,6 @@ int oc_fgmres(oc_ctx* C, const double* b, double* x, double tol, int restart, in
     for (int k = 0; k < jdone; ++k) axpby(1.0, x, yv[k], Z + (size_t)k * len, x, len);
     if (res < tol * bn) { *info = 0; break; }
   }
-  free(V); free(Z); free(w); free(H); free(cs); free(sn); free(g); free(yv);
+  free(V); free(Z); free(w); free(H); free(cs); free(sn); free(g); free(yv); free(bcopy);
   return it;
 }

@@ -27,6 +27,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __grid_constant__
 #define __shared__ static /* blocks run one after another, so a function-local static is block-shared */
 
 struct dim3 {
@@ -151,6 +152,15 @@ inline double __shfl_xor_sync(unsigned, double v, int m) {
   w->xd[lane] = v;
   w->bar.arrive_and_wait();
   const double r = w->xd[lane ^ m];
+  w->bar.arrive_and_wait();
+  return r;
+}
+inline int __shfl_sync(unsigned, int v, int src) {
+  emu::WarpCtx* w = emu::ts().warp;
+  const int lane = (int)(emu::ts().tid.x & 31);
+  w->xd[lane] = (double)v;
+  w->bar.arrive_and_wait();
+  const int r = (int)w->xd[src & 31];
   w->bar.arrive_and_wait();
   return r;
 }

@@ -11,7 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(HERE, "_build", "libmpbp_emu.so")
 SRCS = [os.path.join(HERE, "emu_kernels.cpp"), os.path.join(HERE, "cuda_emu.h"),
         os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "stencil.cuh"),
-        os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "coarse.cuh")]
+        os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "coarse.cuh"),
+        os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "stokes.cuh")]
 _dp = C.POINTER(C.c_double)
 _lib = None
 
@@ -64,6 +65,22 @@ def stokes_fused(variant, n, prm, mass_mode, theta, x, b, wd=None, ec=None, rs=8
     load().emu_stokes_fused(variant, n, _p(prm), mass_mode, _p(thp), _p(x), _p(b), _p(wd), _p(ec), _p(y), rs, pf,
                             C.c_double(omega))
     return y
+
+
+def stokes_x(IN, MODE, EP, n, prm, mass_mode, theta, x, b=None, with_p=False, wd=None, ec=None, d=None, xk=None,
+             cheb=None, flags=(1, 1, 1), rs=8, pf=3, omega=0.8):
+    """csrc/stokes.cuh: k_stokes_x<IN, MODE, WITH_P, EP>.  Returns y (EP 0), (d, xk) (EP 1) or the coarse rhs (EP 2)."""
+    c = lambda v: None if v is None else np.ascontiguousarray(v, dtype=np.float64)
+    x, b, wd, ec = c(x), c(b), c(wd), c(ec)
+    thp = pad_theta(theta)
+    out = np.zeros(n * n if EP == 2 else (5 if with_p else 4) * n * n)
+    if EP == 1:
+        d, xk = np.array(d, dtype=np.float64), np.array(xk, dtype=np.float64)
+    ch = None if cheb is None else np.array(cheb, dtype=np.float64)
+    fl = (C.c_int * 3)(*flags)
+    load().emu_stokes_x(IN, MODE, int(with_p), EP, n, _p(prm), mass_mode, _p(thp), _p(x), _p(b), _p(wd), _p(ec),
+                        _p(d), _p(xk), _p(ch), fl, _p(out), rs, pf, C.c_double(omega))
+    return (d, xk) if EP == 1 else out
 
 
 def jacobi0_F(n, prm, mass_mode, theta, b, rs=8, omega=0.8):

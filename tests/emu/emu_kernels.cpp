@@ -3,6 +3,7 @@
 #define MPBP_EMU 1
 #include "../../mp-block-preconditioners_b200/csrc/stencil.cuh"
 #include "../../mp-block-preconditioners_b200/csrc/coarse.cuh"
+#include "../../mp-block-preconditioners_b200/csrc/stokes.cuh"
 
 using namespace mpbp;
 
@@ -70,6 +71,45 @@ void emu_stokes_fused(int variant, int n, const double* prm, int mass_mode, cons
   emu::launch(sgrid(n, rs), dim3(kBlockThreads), [&] {
     if (variant == 0) k_stokes_fused<0>(in, th_pad, b, y, g, ph, omega, fa);
     else k_stokes_fused<1>(in, th_pad, b, y, g, ph, omega, fa);
+  });
+}
+
+// the unified marching kernel of csrc/stokes.cuh on a whole (periodic) grid.  out: y (EP 0, 4 or 5 fields), nothing
+// (EP 1: d / xk are updated in place), or the coarse rhs (EP 2)
+void emu_stokes_x(int in, int mode, int with_p, int ep, int n, const double* prm, int mass_mode, const double* th_pad,
+                  const double* x, const double* b, const double* wd, const double* ec, double* d, double* xk,
+                  const double* cheb, const int* flags, double* out, int rs, int pf, double omega) {
+  Tables t;
+  StokesArgs a{};
+  a.ph = make_phys(n, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], prm[6], mass_mode, t);
+  a.g = Geo{n, n, 0, rs, pf};
+  a.xin = whole_grid_view(x, n);
+  a.th = th_pad;
+  a.b = b;
+  a.y = out;
+  a.omega = omega;
+  if (wd) a.wd = whole_grid_view(wd, n);
+  if (ec) a.cin = whole_grid_view(ec, n / 2);
+  a.nc = n / 2;
+  a.rows_c = n / 2;
+  if (cheb) a.ce = ChebEp{cheb[0], cheb[1], d, xk, flags[0], flags[1], flags[2]};
+  a.bc = out;
+  const int wc = (ep == 2) ? WarpTile<2>::cols : WarpTile<0>::cols;
+  const dim3 grid((n + wc * kBlockWarps - 1) / (wc * kBlockWarps), (n + rs - 1) / rs);
+  const int key = in * 1000 + mode * 100 + with_p * 10 + ep;
+  emu::launch(grid, dim3(kBlockThreads), [&] {
+    switch (key) {
+      case 10: k_stokes_x<0, 0, true, 0, false, 0>(a); break;
+      case 0: k_stokes_x<0, 0, false, 0, false, 0>(a); break;
+      case 100: k_stokes_x<0, 1, false, 0, false, 0>(a); break;
+      case 200: k_stokes_x<0, 2, false, 0, false, 0>(a); break;
+      case 1200: k_stokes_x<1, 2, false, 0, false, 0>(a); break;
+      case 2200: k_stokes_x<2, 2, false, 0, false, 0>(a); break;
+      case 201: k_stokes_x<0, 2, false, 1, false, 0>(a); break;
+      case 2201: k_stokes_x<2, 2, false, 1, false, 0>(a); break;
+      case 102: k_stokes_x<0, 1, false, 2, false, 0>(a); break;
+      default: break;
+    }
   });
 }
 

@@ -145,25 +145,47 @@ def main():
         out = dict(params=np.array([n, xi, eta_n, eta_s, c, d]), b_vec=b_vec, u_vec=u_vec, v=v, Mv=M.matvec(v),
                    Mb=M.matvec(b_vec), hist=_state["hist"], true_res=np.array(true_res), x=_state["x"],
                    err_norms=np.array(norms))
-        # conditioning of the history itself: re-run with ~1-ulp relative perturbations of b and record
-        # the largest relative change per iteration (the envelope no implementation can beat)
-        def envelope(run, h0):
+        # conditioning of the history itself: what another correct fp64 implementation of the same algorithm may
+        # legitimately return.  16 re-runs in which b AND the result of every A.x and M.v carry an independent
+        # ~1-ulp relative perturbation (a different summation order / fma contraction in any kernel does that);
+        # for FGMRES additionally the independent C restatement of the oracle (its own rounding everywhere).
+        # The envelope is the largest relative change per iteration.
+        import scipy.sparse.linalg as spla
+
+        def noisy(op, prng):
+            f = (lambda z: op @ z) if not hasattr(op, "matvec") else op.matvec
+            return spla.LinearOperator((len(b_vec), len(b_vec)), dtype=np.float64,
+                                       matvec=lambda z: f(z) * (1.0 + 1.2e-16 * prng.standard_normal(len(b_vec))))
+
+        def envelope(run, h0, extra=()):
             env = np.zeros(len(h0))
             prng = np.random.default_rng(99)
-            for _ in range(6):
-                bp_ = b_vec * (1.0 + 1.2e-16 * prng.standard_normal(b_vec.shape))
-                h = run(bp_)
+
+            def fold(h):
                 k = min(len(h), len(h0))
                 env[:k] = np.maximum(env[:k], np.abs(h[:k] - h0[:k]) / h0[:k])
                 if len(h) != len(h0):
                     env[k:] = np.inf
+            for _ in range(16):  # >= 16 perturbed runs per envelope
+                bp_ = b_vec * (1.0 + 1.2e-16 * prng.standard_normal(b_vec.shape))
+                fold(run(bp_, noisy(A, prng), noisy(M, prng)))
+            for h in extra:
+                fold(h)
             return env
 
-        def run_fg(bb):
-            O.fgmres(A, bb, M=M, tol=1e-8, maxiter=150)
+        def run_fg(bb, Aop, Mop):
+            O.fgmres(Aop, bb, M=Mop, tol=1e-8, maxiter=150)
             return O.fgmres.last_history.copy()
 
-        out["hist_sens"] = envelope(run_fg, _state["hist"])
+        import c_oracle
+        ckw = dict(kind=cfgF.kind, F_cycles=cfgF.cycles, P_cycles=cfgF.cycles, F_sweeps=cfgF.sweeps, P_sweeps=cfgF.sweeps,
+                   omega=cfgF.omega, cheb=cfgF.cheb)
+        c_hists = []
+        for threads in (1, 3, 8):
+            c_oracle.set_threads(threads)
+            c_hists.append(c_oracle.COracle(n, xi, eta_n, eta_s, c, d, **ckw).fgmres(b_vec, tol=1e-8, restart=150,
+                                                                                     maxiter=150)[2])
+        out["hist_sens"] = envelope(run_fg, _state["hist"], extra=c_hists)
         # left-preconditioned scipy gmres on the reference's dense A with the same closure
         for restart in (20, 150):
             xs, info, hs = O.gmres_scipy(A, b_vec, M=M, rtol=1e-8, restart=restart, maxiter=40)
@@ -171,7 +193,7 @@ def main():
             out[f"scipy_x_r{restart}"] = xs
             out[f"scipy_info_r{restart}"] = np.array(info)
             out[f"scipy_sens_r{restart}"] = envelope(
-                lambda bb: O.gmres_scipy(A, bb, M=M, rtol=1e-8, restart=restart, maxiter=40)[2], hs)
+                lambda bb, Aop, Mop: O.gmres_scipy(Aop, bb, M=Mop, rtol=1e-8, restart=restart, maxiter=40)[2], hs)
         print("  sens fgmres max", out["hist_sens"].max(), "scipy r20", out["scipy_sens_r20"].max(), "r150",
               out["scipy_sens_r150"].max())
         np.savez_compressed(os.path.join(HERE, f"solve_{tag}_n{n}_eta{int(eta_n)}.npz"), **out)

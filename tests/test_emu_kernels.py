@@ -133,3 +133,49 @@ def test_fused_halo_push_chain_on_the_shim(P, rs):
     x2 = x1 + 0.8 * (b - ops.F @ x1) / dg
     got = emu.slab_fused_push_chain(P, n, prm, theta, x0, b, rs=rs)
     assert relerr(got, b - ops.F @ x2) < 1e-12
+
+
+@pytest.mark.parametrize("n,analytic,rs", [(8, True, 4), (12, False, 6), (32, True, 4), (36, False, 8)])
+def test_unified_marching_kernel_and_its_fused_variants(n, analytic, rs):
+    """csrc/stokes.cuh: every (IN, MODE, EP) instantiation the plan launches, against compositions of the oracle's
+    operators.  n=32/36 with short strips exercise the lean interior instantiation (strips with r0 >= 2 and
+    r1 + 4 <= rows) next to the edge one; n=36 is not a multiple of the warp tile."""
+    theta, ops, prm = _setup(n, analytic)
+    mm = 1 if analytic else 0
+    rng = np.random.default_rng(n + rs)
+    N = n * n
+    x5 = rng.standard_normal(5 * N)
+    x, b = x5[:4 * N], rng.standard_normal(4 * N)
+    dg = ops.F.diagonal()
+    sweep = lambda v: v + 0.8 * (b - ops.F @ v) / dg
+    kw = dict(rs=rs)
+    assert relerr(emu.stokes_x(0, 0, 0, n, prm, mm, theta, x5, with_p=True, **kw), ops.A @ x5) < 1e-13
+    assert relerr(emu.stokes_x(0, 0, 0, n, prm, mm, theta, x, **kw), ops.F @ x) < 1e-13
+    assert relerr(emu.stokes_x(0, 1, 0, n, prm, mm, theta, x, b, **kw), b - ops.F @ x) < 1e-13
+    assert relerr(emu.stokes_x(0, 2, 0, n, prm, mm, theta, x, b, **kw), sweep(x)) < 1e-13
+    # IN 1: both pre-smoothing sweeps from a zero guess in one pass
+    x1 = 0.8 * b / dg
+    assert relerr(emu.stokes_x(1, 2, 0, n, prm, mm, theta, b, b, wd=0.8 / dg, **kw), sweep(x1)) < 1e-13
+    # IN 2: coarse-grid correction + first post-smoothing sweep
+    ec = rng.standard_normal(N)
+    e4 = ec.reshape(4, n // 2, n // 2)
+    xt = x + np.concatenate([O.prolong_u(e4[0]).ravel(), O.prolong_v(e4[1]).ravel(), O.prolong_u(e4[2]).ravel(),
+                             O.prolong_v(e4[3]).ravel()])
+    assert relerr(emu.stokes_x(2, 2, 0, n, prm, mm, theta, x, b, ec=ec, **kw), sweep(xt)) < 1e-13
+    # EP 1: last sweep + Chebyshev update (z never stored): later cycle, first cycle, last cycle
+    d0, xk0 = rng.standard_normal(4 * N), rng.standard_normal(4 * N)
+    z = sweep(x)
+    d1, xk1 = emu.stokes_x(0, 2, 1, n, prm, mm, theta, x, b, d=d0, xk=xk0, cheb=(0.3, 1.7), flags=(1, 1, 1), **kw)
+    assert relerr(d1, 0.3 * d0 + 1.7 * z) < 1e-13 and relerr(xk1, xk0 + 0.3 * d0 + 1.7 * z) < 1e-13
+    d1, xk1 = emu.stokes_x(0, 2, 1, n, prm, mm, theta, x, b, d=d0, xk=xk0, cheb=(0.0, 1.7), flags=(0, 0, 1), **kw)
+    assert relerr(d1, 1.7 * z) < 1e-13 and relerr(xk1, 1.7 * z) < 1e-13
+    d1, xk1 = emu.stokes_x(0, 2, 1, n, prm, mm, theta, x, b, d=d0, xk=xk0, cheb=(0.3, 1.7), flags=(1, 1, 0), **kw)
+    assert np.array_equal(d1, d0) and relerr(xk1, xk0 + 0.3 * d0 + 1.7 * z) < 1e-13
+    # IN 2 + EP 1 (V(2,1)-style cycles: the only post-sweep is also the last one)
+    d1, xk1 = emu.stokes_x(2, 2, 1, n, prm, mm, theta, x, b, ec=ec, d=d0, xk=xk0, cheb=(0.3, 1.7), **kw)
+    assert relerr(xk1, xk0 + 0.3 * d0 + 1.7 * sweep(xt)) < 1e-13
+    # EP 2: residual + full-weighting restriction (only the coarse rhs is stored)
+    r4 = (b - ops.F @ x).reshape(4, n, n)
+    ref_r = np.concatenate([O.restrict_u(r4[0]).ravel(), O.restrict_v(r4[1]).ravel(), O.restrict_u(r4[2]).ravel(),
+                            O.restrict_v(r4[3]).ravel()])
+    assert relerr(emu.stokes_x(0, 1, 2, n, prm, mm, theta, x, b, **kw), ref_r) < 1e-13

@@ -7,7 +7,7 @@ import pytest
 import scipy.sparse as sp
 
 import mpbp_oracle as O
-from conftest import golden, relerr
+from conftest import golden, hist_check, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -151,17 +151,6 @@ def test_precond_apply_vs_reference_closure(mp, fx, subkw):
     assert relerr(M.matvec_host(v), g["Mv"]) < 1e-9
 
 
-def _hist_excess(h, ref, sens):
-    """Largest ratio (relative deviation of the history) / (allowed deviation).  Allowed = 1e-10 relative
-    (BASELINE.json) wherever the oracle's own history is reproducible to that level; where the oracle
-    itself moves by `sens` under 1-ulp perturbations of b (recorded in the fixture), 1000 x sens."""
-    k = min(len(h), len(ref))
-    assert abs(len(h) - len(ref)) <= 1, (len(h), len(ref))
-    rel = np.abs(h[:k] - ref[:k]) / ref[:k]
-    allowed = np.maximum(1e-10, 1e3 * sens[:k])
-    return (rel / allowed).max()
-
-
 @pytest.mark.parametrize("fx,subkw", SOLVES)
 def test_fgmres_history_vs_reference_run(mp, fx, subkw):
     """Right-preconditioned FGMRES (solve.py:285) residual history, iterate and error norms vs the golden
@@ -172,9 +161,7 @@ def test_fgmres_history_vs_reference_run(mp, fx, subkw):
     u, info, hist = mp.solve_with_approx_schur_pc(n, xi, eta_n, eta_s, c, d, g["b_vec"], g["u_vec"],
                                                   sub_solver=mp.SubSolver(**subkw), verbose=False)
     assert info == 0
-    assert _hist_excess(hist, g["hist"], g["hist_sens"]) < 1.0
-    if g["hist_sens"].max() < 1e-9:
-        assert np.abs(hist - g["hist"][:len(hist)]).max() / 1.0 < 1e-10 * g["hist"][0] + 1e-10 * np.abs(hist).max()
+    hist_check(hist, g["hist"], g["hist_sens"], label=f"fgmres {fx}")
     # both runs stop at ||r|| < 1e-8 ||b||; the iterates agree to that accuracy times the conditioning
     assert relerr(u, g["x"]) < 1e-5
     ops = O.Operators(n, xi, eta_n, eta_s, c, d)
@@ -198,7 +185,7 @@ def test_gmres_left_history_vs_scipy(mp, fx, subkw, restart):
                        callback_type="pr_norm")
     ref = g[f"scipy_hist_r{restart}"]
     assert info == int(g[f"scipy_info_r{restart}"])
-    assert _hist_excess(np.array(hist), ref, g[f"scipy_sens_r{restart}"]) < 1.0
+    hist_check(hist, ref, g[f"scipy_sens_r{restart}"], label=f"gmres_left r{restart} {fx}")
     assert relerr(x, g[f"scipy_x_r{restart}"]) < 1e-5
 
 
@@ -214,8 +201,8 @@ def test_true_residual_callback(mp):
     x, info = mp.fgmres(A, g["b_vec"], M=M, tol=1e-8, maxiter=150, callback=mp.print_true_res_norm(A, g["b_vec"], out, verbose=False))
     assert len(out) == len(g["true_res"])
     out = np.array(out)
-    allowed = np.maximum(1e-6, 1e3 * g["hist_sens"][:len(out)])
-    assert (np.abs(out - g["true_res"]) / g["true_res"] / allowed).max() < 1.0
+    # the true residual ||b - A x_k|| carries an O(eps * cond) floor the recurrence residual does not: 1e-6 strict level
+    hist_check(out, g["true_res"], g["hist_sens"][:len(out)], label="true residual", strict_rel=1e-6)
     # the recurrence residual the solver reports tracks the true residual (right preconditioning)
     assert np.allclose(out, mp.fgmres.last_history, rtol=1e-3)
 
@@ -233,10 +220,10 @@ def test_unpreconditioned_matches_oracle(mp):
     # conditioning of the oracle's own history under 1-ulp perturbations of b
     sens = np.zeros(100)
     prng = np.random.default_rng(5)
-    for _ in range(4):
+    for _ in range(16):
         O.fgmres(ops.A, b_vec * (1 + 1.2e-16 * prng.standard_normal(b_vec.shape)), M=None, tol=1e-8, maxiter=100)
         sens = np.maximum(sens, np.abs(O.fgmres.last_history - ho) / ho)
-    assert _hist_excess(h, ho, sens) < 1.0
+    hist_check(h, ho, sens, label="unpreconditioned")
     assert np.allclose(h[:20], ho[:20], rtol=1e-9)
 
 
