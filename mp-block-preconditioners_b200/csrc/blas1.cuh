@@ -313,4 +313,24 @@ __global__ void __launch_bounds__(256) k_cheb_update(double a, double b, const d
   }
 }
 
+// Chebyshev / iteration update as a stand-alone pass (only where no smoothing sweep can carry it as its epilogue:
+// single-level hierarchies): d = ca*d + cb*z ; xk += d
+__global__ void __launch_bounds__(256) k_cheb_ep(double ca, double cb, const double* __restrict__ z, double* __restrict__ d,
+                                                 double* __restrict__ xk, int read_d, int read_x, int write_d, size_t len) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+    const double dn = ca * (read_d ? d[i] : 0.0) + cb * z[i];
+    if (write_d) d[i] = dn;
+    xk[i] = (read_x ? xk[i] : 0.0) + dn;
+  }
+}
+
+// z = [w - y ; xp]: the last two lines of approx_schur_op (solve.py:275-276)
+__global__ void __launch_bounds__(256) k_combine(const double* __restrict__ w, const double* __restrict__ y,
+                                                 const double* __restrict__ xp, double* __restrict__ z, size_t n4, size_t n1) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4 + n1; i += stride)
+    z[i] = (i < n4) ? 1.0 * w[i] + (-1.0) * y[i] : xp[i - n4];
+}
+
 }  // namespace mpbp

@@ -19,6 +19,7 @@
 #include "blas1.cuh"
 #include "coarse.cuh"
 #include "stencil.cuh"
+#include "stokes.cuh"
 
 using namespace mpbp;
 
@@ -97,7 +98,8 @@ struct mpbp_plan {
   // level-0 scratch
   double *w = nullptr, *g = nullptr, *t2 = nullptr;                 // 4N
   double *rinF = nullptr, *zF = nullptr, *dvF = nullptr;            // 4N
-  double *rhs = nullptr, *xa = nullptr, *xb = nullptr;              // N
+  double *rhs = nullptr, *xa = nullptr, *xb = nullptr, *xp = nullptr;  // N
+  double* vin = nullptr;                                            // 5N: copy of the apply's input (graph-fixed address)
   double *rinP = nullptr, *zP = nullptr, *dvP = nullptr;            // N
   // reductions
   double* partial = nullptr;
@@ -116,9 +118,9 @@ struct mpbp_plan {
   cudaStream_t own = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   // V-cycles (rin -> z) replay as CUDA graphs: ~100 small launches per cycle become one graph launch
-  // bit 0: fused pre-smoothing pair (default: -10 % V-cycle time), bit 1: fused prolongation + first post-sweep
-  // (128 registers, measured slower: off) -- whole-grid levels only, MPBP_FUSE overrides
-  int fuse = 1;
+  // whole-grid levels, MPBP_FUSE overrides: bit 0 fused pre-smoothing pair, bit 1 fused prolongation + first
+  // post-sweep, bit 2 fused residual + restriction (csrc/stokes.cuh)
+  int fuse = 7;
   // experimental (MPBP_PUSH_FUSED=1): smoothing / residual kernels on distributed levels push their own boundary
   // rows to the neighbours; the next stencil kernel on that vector then skips its k_halo_push
   bool push_fused = false;
@@ -127,8 +129,8 @@ struct mpbp_plan {
   bool fused_mgs = true;
   int jac_minb = 0;  // __launch_bounds__ min blocks/SM variant of the Jacobi kernel (register cap)
   bool use_graph = true;
-  cudaGraphExec_t gexec[2] = {nullptr, nullptr};
-  long long glaunches[2] = {0, 0};
+  cudaGraphExec_t gexec_apply = nullptr;  // the whole preconditioner apply (vin -> w, t2, xp)
+  long long glaunches_apply = 0;
   // ---- peer-memory halo exchange (nranks > 1): ring neighbours push rows into this rank's comm buffer ----
   bool p2p = false;
   char* comm_local = nullptr;               // cudaMalloc'd, exported with cudaIpc
@@ -177,6 +179,8 @@ static int build_levels_shape(const mpbp_config& c, std::vector<Level>& lev, int
   if (P > 1 && lev.back().dist && !c.operators_only)
     return set_err(MPBP_E_UNSUPPORTED, "nranks>1 needs at least one coarsening step (n=%d, n_coarse=%d)", c.n, c.n_coarse);
   if ((int)lev.size() > 1 && (c.nu1 < 1 || c.nu2 < 0)) return set_err(MPBP_E_ARG, "need nu1>=1, nu2>=0");
+  if (5.0 * (double)lev[0].rows * (double)lev[0].n >= 2147483647.0)
+    return set_err(MPBP_E_UNSUPPORTED, "slab of %d x %d cells exceeds the 32-bit element offsets of the kernels", lev[0].rows, lev[0].n);
   return 0;
 }
 
@@ -214,6 +218,8 @@ static void carve(mpbp_plan* p, Bump& B) {
   p->rhs = B.take<double>(fs0);
   p->xa = B.take<double>(fs0);
   p->xb = B.take<double>(fs0);
+  p->xp = B.take<double>(fs0);
+  p->vin = B.take<double>(5 * fs0);
   p->rinP = B.take<double>(fs0);
   p->zP = B.take<double>(fs0);
   p->dvP = B.take<double>(fs0);
@@ -248,7 +254,8 @@ static int choose_rs(int gx, int rows, int cap) {
   if ((long long)gx * s32 >= 4LL * cap) return 32;
   double best = -1.0;
   int best_rs = std::min(rows, 32);
-  for (int rs = 4; rs <= std::min(rows, 64); ++rs) {
+  const int inc = (rows & 1) ? 1 : 2;  // even strips on even grids: the row-pair kernels (stokes.cuh IN 2 / EP 2) need them
+  for (int rs = 4; rs <= std::min(rows, 64); rs += inc) {
     const int S = (rows + rs - 1) / rs;
     const long long B = (long long)gx * S;
     const long long waves = (B + cap - 1) / cap;
@@ -328,32 +335,66 @@ static int allreduce_scal(mpbp_plan* p, double* dev, int count) {
 }
 
 // ---- operator launches -----------------------------------------------------------------------
-static int op_stokes(mpbp_plan* p, int l, int mode, bool with_p, const double* x, const double* b, double* y,
-                     double omega) {
+// one launch of the unified marching kernel (csrc/stokes.cuh); `a` carries the variant's extra arguments
+struct SxKind {
+  int in = 0, mode = 0, ep = 0;
+  bool with_p = false, push = false;
+};
+template <int IN, int MODE, bool WP, int EP, bool PUSH, int MINB>
+static void sx_launch(mpbp_plan* p, dim3 grid, const StokesArgs& a) {
+  k_stokes_x<IN, MODE, WP, EP, PUSH, MINB><<<grid, kBlockThreads, 0, p->st>>>(a);
+}
+static int launch_sx(mpbp_plan* p, int l, SxKind k, StokesArgs& a) {
   Level& v = p->lev[l];
-  VecIn in{};
-  RET(make_view(p, v, x, with_p ? 5 : 4, in));
-  const dim3 grid = stencil_grid(v, v.geo), block(kBlockThreads);
-  if (with_p)
-    k_stokes<0, true><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega);
-  else if (mode == 0)
-    k_stokes<0, false><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega);
-  else if (v.dist && p->p2p && p->push_fused) {
-    const PushOut po{p->comm_prev, p->comm_next, p->comm_area, p->dseq, p->counter + 40};
-    if (mode == 1) k_stokes_push<1><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega, po);
-    else k_stokes_push<2><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega, po);
-    LAUNCH_CHECK(p);
-    p->pending_push = y;
-    return 0;
-  } else if (mode == 1)
-    k_stokes<1, false><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega);
-  else if (p->jac_minb == 6)
-    k_stokes<2, false, 6><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega);
-  else if (p->jac_minb == 7)
-    k_stokes<2, false, 7><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega);
-  else
-    k_stokes<2, false><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega);
+  a.th = v.th;
+  a.g = v.geo;
+  a.ph = v.ph;
+  const int wc = (k.ep == 2) ? WarpTile<2>::cols : WarpTile<0>::cols;
+  if ((k.in == 2 || k.ep == 2) && ((v.rows & 1) || (v.geo.rs & 1) || v.dist))
+    return set_err(MPBP_E_STATE, "internal: row-pair kernel on an odd / distributed level (rows %d, rs %d)", v.rows, v.geo.rs);
+  const dim3 grid((unsigned)((v.n + wc * kBlockWarps - 1) / (wc * kBlockWarps)), (unsigned)((v.rows + v.geo.rs - 1) / v.geo.rs));
+  if (k.push) a.po = PushOut{p->comm_prev, p->comm_next, p->comm_area, p->dseq, p->counter + 40};
+  const int key = k.in * 10000 + k.mode * 1000 + (k.with_p ? 100 : 0) + k.ep * 10 + (k.push ? 1 : 0);
+  switch (key) {
+    case 100: sx_launch<0, 0, true, 0, false, 5>(p, grid, a); break;    // y = A x
+    case 0: sx_launch<0, 0, false, 0, false, 5>(p, grid, a); break;      // y = F x
+    case 1000: sx_launch<0, 1, false, 0, false, 5>(p, grid, a); break;   // residual
+    case 1001: sx_launch<0, 1, false, 0, true, 5>(p, grid, a); break;
+    case 2000: sx_launch<0, 2, false, 0, false, 5>(p, grid, a); break;   // Jacobi sweep
+    case 2001: sx_launch<0, 2, false, 0, true, 5>(p, grid, a); break;
+    case 2010: sx_launch<0, 2, false, 1, false, 5>(p, grid, a); break;   // last sweep + Chebyshev update
+    case 2011: sx_launch<0, 2, false, 1, true, 5>(p, grid, a); break;
+    case 12000: sx_launch<1, 2, false, 0, false, 5>(p, grid, a); break;  // pre-smoothing pair from b
+    case 12001: sx_launch<1, 2, false, 0, true, 5>(p, grid, a); break;
+    case 1020: sx_launch<0, 1, false, 2, false, 5>(p, grid, a); break;   // residual + restriction
+    case 22000: sx_launch<2, 2, false, 0, false, 4>(p, grid, a); break;  // prolongation + first post-sweep
+    case 22010: sx_launch<2, 2, false, 1, false, 4>(p, grid, a); break;  // ... which is also the last one
+    default: return set_err(MPBP_E_STATE, "internal: no stokes kernel variant %d", key);
+  }
   LAUNCH_CHECK(p);
+  return 0;
+}
+
+// y = Op x (mode 0), b - F x (mode 1), x + omega (b - F x)/diag (mode 2); optional Chebyshev epilogue on mode 2.
+// On distributed levels the smoothing / residual kernels push their own boundary rows to the ring neighbours.
+static int op_stokes(mpbp_plan* p, int l, int mode, bool with_p, const double* x, const double* b, double* y,
+                     double omega, const ChebEp* ce = nullptr) {
+  Level& v = p->lev[l];
+  StokesArgs a{};
+  RET(make_view(p, v, x, with_p ? 5 : 4, a.xin));
+  a.b = b;
+  a.y = y;
+  a.omega = omega;
+  SxKind k;
+  k.mode = mode;
+  k.with_p = with_p;
+  if (ce) {
+    a.ce = *ce;
+    k.ep = 1;
+  }
+  k.push = v.dist && p->p2p && p->push_fused && mode != 0;
+  RET(launch_sx(p, l, k, a));
+  if (k.push) p->pending_push = ce ? ce->xk : y;
   return 0;
 }
 static int op_jacobi0_F(mpbp_plan* p, int l, const double* b, double* y, double omega) {
@@ -362,34 +403,74 @@ static int op_jacobi0_F(mpbp_plan* p, int l, const double* b, double* y, double 
   LAUNCH_CHECK(p);
   return 0;
 }
-// fused smoothing kernels (whole-grid levels only): variant 0 = two pre-smoothing sweeps from zero out of b,
-// variant 1 = x + P e_c followed by one sweep
-static int op_stokes_fused(mpbp_plan* p, int l, int variant, const double* x, const double* b, double* y,
-                           double omega) {
+// x2 = x1 + wd (b - F x1), x1 = wd b: the two pre-smoothing sweeps from a zero guess in one pass over b
+static int op_presmooth_pair(mpbp_plan* p, int l, const double* b, double* y) {
   Level& v = p->lev[l];
-  if (v.dist) return set_err(MPBP_E_STATE, "internal: fused smoothing on a distributed level");
-  VecIn in{};
-  RET(make_view(p, v, x, 4, in));
-  FuseArgs fa{};
-  if (variant == 0) {
-    RET(make_view(p, v, v.wdF, 4, fa.wd));
-  } else {
-    fa.ec = p->lev[l + 1].xF;
-  }
-  fa.nc = v.n / 2;
-  const dim3 grid = stencil_grid(v, v.geo), block(kBlockThreads);
-  if (variant == 0)
-    k_stokes_fused<0><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega, fa);
-  else
-    k_stokes_fused<1><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geo, v.ph, omega, fa);
-  LAUNCH_CHECK(p);
-  return 0;
+  StokesArgs a{};
+  RET(make_view(p, v, b, 4, a.xin));
+  a.wd = a.xin;
+  a.wd.x = v.wdF;
+  if (v.dist) return set_err(MPBP_E_STATE, "internal: fused pre-smoothing on a distributed level");
+  a.wd.top = v.wdF + (size_t)(v.rows - 1) * v.n;
+  a.wd.bot = v.wdF;
+  a.y = y;
+  SxKind k;
+  k.in = 1;
+  k.mode = 2;
+  return launch_sx(p, l, k, a);
 }
-static int op_poisson(mpbp_plan* p, int l, int mode, const double* x, const double* b, double* y, double omega) {
+// coarse rhs b_{l+1} = R (b - F x): residual and full-weighting restriction in one pass (whole-grid levels)
+static int op_residual_restrict(mpbp_plan* p, int l, const double* x, const double* b) {
+  Level& v = p->lev[l];
+  Level& c = p->lev[l + 1];
+  StokesArgs a{};
+  RET(make_view(p, v, x, 4, a.xin));
+  a.b = b;
+  a.bc = c.bF;
+  a.nc = c.n;
+  a.rows_c = c.rows;
+  SxKind k;
+  k.mode = 1;
+  k.ep = 2;
+  return launch_sx(p, l, k, a);
+}
+// y = xt + omega (b - F xt)/diag, xt = x + P x_{l+1}: coarse-grid correction + first post-smoothing sweep in one pass
+static int op_prolong_sweep(mpbp_plan* p, int l, const double* x, const double* b, double* y, double omega,
+                            const ChebEp* ce) {
+  Level& v = p->lev[l];
+  Level& c = p->lev[l + 1];
+  StokesArgs a{};
+  RET(make_view(p, v, x, 4, a.xin));
+  a.cin.x = c.xF;
+  a.cin.fs = a.cin.hs = c.fs();
+  a.cin.top = c.xF + (size_t)(c.rows - 1) * c.n;
+  a.cin.bot = c.xF;
+  a.nc = c.n;
+  a.rows_c = c.rows;
+  a.b = b;
+  a.y = y;
+  a.omega = omega;
+  SxKind k;
+  k.in = 2;
+  k.mode = 2;
+  if (ce) {
+    a.ce = *ce;
+    k.ep = 1;
+  }
+  return launch_sx(p, l, k, a);
+}
+static int op_poisson(mpbp_plan* p, int l, int mode, const double* x, const double* b, double* y, double omega,
+                      const ChebEp* ce = nullptr) {
   Level& v = p->lev[l];
   VecIn in{};
   if (mode != 3) RET(make_view(p, v, x, 1, in));
   const dim3 grid = stencil_grid(v, v.geoL), block(kBlockThreads);
+  if (ce) {
+    if (mode != 2) return set_err(MPBP_E_STATE, "internal: Chebyshev epilogue on a non-sweep");
+    k_poisson<2, true><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geoL, v.ph, omega, *ce);
+    LAUNCH_CHECK(p);
+    return 0;
+  }
   switch (mode) {
     case 0: k_poisson<0><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geoL, v.ph, omega); break;
     case 1: k_poisson<1><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geoL, v.ph, omega); break;
@@ -653,28 +734,42 @@ static int coarse_vcycle_launch(mpbp_plan* p, int l, bool isF, const double* b, 
 }
 
 // x = V b: one V(nu1,nu2) cycle from a zero guess.  x must not alias the level's t/r buffers.
-static int vcycle(mpbp_plan* p, int l, bool isF, const double* b, double* x) {
+// With `ce` (level 0 of a sub-solve) the cycle's output z is never stored: the last smoothing sweep feeds it
+// straight into the Chebyshev / iteration update d = ca d + cb z, xk += d, and `x` is only scratch.
+static int vcycle(mpbp_plan* p, int l, bool isF, const double* b, double* x, const ChebEp* ce = nullptr) {
   const mpbp_config& c = p->cfg;
   if (c.operators_only) return set_err(MPBP_E_STATE, "plan was created with operators_only");
   Level& v = p->lev[l];
   const int L = (int)p->lev.size();
-  if (p->coarse_n > 0 && !v.dist && v.n <= p->coarse_n && l < L - 1 && (L - l) <= kCoarseMaxLevels)
+  if (!ce && p->coarse_n > 0 && !v.dist && v.n <= p->coarse_n && l < L - 1 && (L - l) <= kCoarseMaxLevels)
     return coarse_vcycle_launch(p, l, isF, b, x);
   if (l == L - 1) {
     // coarsest level: dense inverse (F) / pseudo-inverse (GtG)
-    return isF ? op_dense(p, p->FinvT, b, x, p->mF) : op_dense(p, p->PinvT, b, x, p->mP);
+    RET(isF ? op_dense(p, p->FinvT, b, x, p->mF) : op_dense(p, p->PinvT, b, x, p->mP));
+    if (ce) {  // single-level hierarchy: no sweep to carry the update
+      const size_t len = (isF ? 4 : 1) * v.fs();
+      k_cheb_ep<<<ew_blocks(len), 256, 0, p->st>>>(ce->ca, ce->cb, x, ce->d, ce->xk, ce->read_d, ce->read_x, ce->write_d, len);
+      LAUNCH_CHECK(p);
+    }
+    return 0;
   }
   double* t = isF ? v.tF : v.tP;
   double* r = isF ? v.rF : v.rP;
-  const int S = (c.nu1 - 1) + c.nu2;
-  double* cur = (S % 2 == 0) ? x : t;
-  double* oth = (cur == x) ? t : x;
+  const bool even = !(v.rows & 1) && !(v.geo.rs & 1);
   const bool fuse_pre = isF && (p->fuse & 1) && !v.dist && c.nu1 == 2 && v.wdF != nullptr;
-  const bool fuse_post = isF && (p->fuse & 2) && !v.dist && c.nu2 >= 1;
+  const bool fuse_rr = isF && (p->fuse & 4) && !v.dist && even;                 // residual + restriction
+  const bool fuse_post = isF && (p->fuse & 2) && !v.dist && even && c.nu2 >= 1;  // prolongation + first post-sweep
+  // number of kernels that write the iterate into a fresh buffer (they ping-pong between x and t); the last one
+  // must land in x unless it ends in the epilogue
+  const int pre_w = fuse_pre ? 1 : c.nu1;
+  const int post_w = c.nu2;  // unfused: prolongation is in place, then nu2 sweeps; fused: nu2 kernels as well
+  const int W = pre_w + post_w - ((ce && post_w > 0) ? 1 : 0);
+  double* cur = (W % 2 == 1) ? x : t;
+  double* oth = (cur == x) ? t : x;
+  if (c.nu2 == 0 && ce) return set_err(MPBP_E_UNSUPPORTED, "nu2 = 0 is not supported inside the sub-solves");
+  // ---- pre-smoothing from a zero guess ----
   if (fuse_pre) {
-    // x2 straight from b: lands where the unfused jacobi0 + sweep would have left it
-    RET(op_stokes_fused(p, l, 0, b, b, oth, c.omega));
-    std::swap(cur, oth);
+    RET(op_presmooth_pair(p, l, b, cur));
   } else {
     if (isF) RET(op_jacobi0_F(p, l, b, cur, c.omega));
     else RET(op_poisson(p, l, 3, nullptr, b, cur, c.omega));
@@ -684,52 +779,33 @@ static int vcycle(mpbp_plan* p, int l, bool isF, const double* b, double* x) {
       std::swap(cur, oth);
     }
   }
-  if (isF) RET(op_stokes(p, l, 1, false, cur, b, r, 0.0));
-  else RET(op_poisson(p, l, 1, cur, b, r, 0.0));
-  RET(op_restrict(p, l, isF, r));
+  // ---- coarse-grid correction ----
+  if (fuse_rr) {
+    RET(op_residual_restrict(p, l, cur, b));
+  } else {
+    if (isF) RET(op_stokes(p, l, 1, false, cur, b, r, 0.0));
+    else RET(op_poisson(p, l, 1, cur, b, r, 0.0));
+    RET(op_restrict(p, l, isF, r));
+  }
   Level& cl = p->lev[l + 1];
   RET(vcycle(p, l + 1, isF, isF ? cl.bF : cl.bP, isF ? cl.xF : cl.xP));
+  // ---- post-smoothing ----
   int post = c.nu2;
   if (fuse_post) {
-    RET(op_stokes_fused(p, l, 1, cur, b, oth, c.omega));
+    const bool last = (post == 1);
+    RET(op_prolong_sweep(p, l, cur, b, oth, c.omega, (last && ce) ? ce : nullptr));
     std::swap(cur, oth);
     post--;
   } else {
     RET(op_prolong_add(p, l, isF, cur));
   }
   for (int s = 0; s < post; ++s) {
-    if (isF) RET(op_stokes(p, l, 2, false, cur, b, oth, c.omega));
-    else RET(op_poisson(p, l, 2, cur, b, oth, c.omega));
+    const ChebEp* e = (s == post - 1) ? ce : nullptr;
+    if (isF) RET(op_stokes(p, l, 2, false, cur, b, oth, c.omega, e));
+    else RET(op_poisson(p, l, 2, cur, b, oth, c.omega, e));
     std::swap(cur, oth);
   }
-  if (cur != x) return set_err(MPBP_E_STATE, "internal: V-cycle ping-pong parity");
-  return 0;
-}
-
-// V-cycle on the fixed internal buffers rin -> z, replayed as a CUDA graph after the first capture
-static int vcycle_fixed(mpbp_plan* p, bool isF) {
-  const double* rin = isF ? p->rinF : p->rinP;
-  double* z = isF ? p->zF : p->zP;
-  if (!p->use_graph) return vcycle(p, 0, isF, rin, z);
-  const int idx = isF ? 0 : 1;
-  if (!p->gexec[idx]) {
-    const long long l0 = p->launches;
-    CU(cudaStreamBeginCapture(p->st, cudaStreamCaptureModeThreadLocal));
-    const int rc = vcycle(p, 0, isF, rin, z);
-    cudaGraph_t g = nullptr;
-    const cudaError_t e = cudaStreamEndCapture(p->st, &g);
-    if (rc != 0) {
-      if (g) cudaGraphDestroy(g);
-      return rc;
-    }
-    CU(e);
-    CU(cudaGraphInstantiate(&p->gexec[idx], g, 0));
-    cudaGraphDestroy(g);
-    p->glaunches[idx] = p->launches - l0;
-    p->launches = l0;
-  }
-  CU(cudaGraphLaunch(p->gexec[idx], p->st));
-  p->launches += p->glaunches[idx];
+  if (!ce && cur != x) return set_err(MPBP_E_STATE, "internal: V-cycle ping-pong parity");
   return 0;
 }
 
@@ -746,11 +822,12 @@ static int project_mean(mpbp_plan* p, double* x) {
   return 0;
 }
 
-// x = F~^-1 b  /  x = (GtG)~^-1 b  (fixed linear operators; zero initial guess)
+// x = F~^-1 b  /  x = (GtG)~^-1 b  (fixed linear operators; zero initial guess).  b is never copied and the V-cycle
+// outputs are never materialised: cycle k runs on rhs_k (b, then the residual b - Op x) and its last sweep applies
+// the update x += d_k directly (plain iteration: d = z; Chebyshev semi-iteration over [lmin, lmax]: d = ca d + cb z).
 static int sub_solve(mpbp_plan* p, bool isF, const double* b, double* x) {
   const mpbp_config& c = p->cfg;
   Level& v = p->lev[0];
-  const size_t len = (isF ? 4 : 1) * v.fs();
   const int kind = isF ? c.F_kind : c.P_kind;
   if (c.operators_only) return set_err(MPBP_E_STATE, "plan was created with operators_only");
   if (kind == MPBP_SUB_JACOBI) {
@@ -763,35 +840,41 @@ static int sub_solve(mpbp_plan* p, bool isF, const double* b, double* x) {
     const int cycles = isF ? c.F_cycles : c.P_cycles;
     if (cycles < 1) return set_err(MPBP_E_ARG, "cycles must be >= 1");
     double* rin = isF ? p->rinF : p->rinP;
-    double* z = isF ? p->zF : p->zP;
+    double* z = isF ? p->zF : p->zP;  // scratch of the level-0 cycle
     double* dv = isF ? p->dvF : p->dvP;
-    RET(v_copy(p, b, rin, len));  // every cycle runs rin -> z on fixed buffers (graph replay)
-    if (!c.cheb) {
-      RET(vcycle_fixed(p, isF));
-      RET(v_copy(p, z, x, len));
-      for (int k = 1; k < cycles; ++k) {
-        if (isF) RET(op_stokes(p, 0, 1, false, x, b, rin, 0.0));
-        else RET(op_poisson(p, 0, 1, x, b, rin, 0.0));
-        RET(vcycle_fixed(p, isF));
-        RET(v_axpby(p, 1.0, x, 1.0, z, x, len));
-      }
-    } else {
-      // Chebyshev semi-iteration on (V-cycle) o A, spectrum in [lmin, lmax]
-      const double th = 0.5 * (c.lmax + c.lmin), de = 0.5 * (c.lmax - c.lmin);
-      const double sig = th / de;
-      double rho_k = 1.0 / sig;
-      RET(vcycle_fixed(p, isF));
-      RET(v_axpby(p, 1.0 / th, z, 0.0, z, dv, len));
-      RET(v_copy(p, dv, x, len));
-      for (int k = 1; k < cycles; ++k) {
-        if (isF) RET(op_stokes(p, 0, 1, false, x, b, rin, 0.0));
-        else RET(op_poisson(p, 0, 1, x, b, rin, 0.0));
-        RET(vcycle_fixed(p, isF));
+    const double th = 0.5 * (c.lmax + c.lmin), de = 0.5 * (c.lmax - c.lmin);
+    const double sig = th / de;
+    double rho_k = 1.0 / sig;
+    for (int k = 0; k < cycles; ++k) {
+      ChebEp ce{};
+      ce.d = dv;
+      ce.xk = x;
+      ce.read_x = k > 0;
+      if (!c.cheb) {
+        ce.ca = 0.0;
+        ce.cb = 1.0;  // x += z
+        ce.read_d = 0;
+        ce.write_d = 0;
+      } else if (k == 0) {
+        ce.ca = 0.0;
+        ce.cb = 1.0 / th;  // d = z / theta ; x = d
+        ce.read_d = 0;
+        ce.write_d = cycles > 1;
+      } else {
         const double rho_n = 1.0 / (2.0 * sig - rho_k);
-        k_cheb_update<<<ew_blocks(len), 256, 0, p->st>>>(rho_n * rho_k, 2.0 * rho_n / de, z, dv, x, len);
-        LAUNCH_CHECK(p);
+        ce.ca = rho_n * rho_k;
+        ce.cb = 2.0 * rho_n / de;
+        ce.read_d = 1;
+        ce.write_d = k < cycles - 1;
         rho_k = rho_n;
       }
+      const double* rhs = b;
+      if (k > 0) {
+        if (isF) RET(op_stokes(p, 0, 1, false, x, b, rin, 0.0));
+        else RET(op_poisson(p, 0, 1, x, b, rin, 0.0));
+        rhs = rin;
+      }
+      RET(vcycle(p, 0, isF, rhs, z, &ce));
     }
   }
   if (!isF && c.project) RET(project_mean(p, x));
@@ -801,18 +884,53 @@ static int sub_solve(mpbp_plan* p, bool isF, const double* b, double* x) {
 // ---------------------------------------------------------------------------------------------
 // the preconditioner apply: approx_schur_op, solve.py:257-277
 // ---------------------------------------------------------------------------------------------
-static int precond_apply(mpbp_plan* p, const double* v, double* z) {
+// everything of the apply that runs on plan-internal buffers: vin -> (w, t2, xp)
+static int precond_core(mpbp_plan* p) {
   const size_t fs = p->lev[0].fs();
+  const double* v = p->vin;
   RET(sub_solve(p, true, v, p->w));                       // :258  Finv_v = F_inv @ v[:4N]
   RET(op_div(p, 0, p->w, v + 4 * fs, p->rhs, 1.0));       // :259  rhs_interim = D Finv_v + v[4N:]
   RET(sub_solve(p, false, p->rhs, p->xa));                // :265  x_a = (GtG)~^-1 rhs_interim
   RET(op_grad(p, 0, p->xa, p->g));                        // :267  x_b = Gt_F_G x_a = -D F G x_a   (:246-249)
   RET(op_stokes(p, 0, 0, false, p->g, nullptr, p->t2, 0.0));
   RET(op_div(p, 0, p->t2, nullptr, p->xb, -1.0));
-  RET(sub_solve(p, false, p->xb, z + 4 * fs));            // :271  x_p = (GtG)~^-1 x_b
-  RET(op_grad(p, 0, z + 4 * fs, p->g));                   // :273  G_xp = G x_p
+  RET(sub_solve(p, false, p->xb, p->xp));                 // :271  x_p = (GtG)~^-1 x_b
+  RET(op_grad(p, 0, p->xp, p->g));                        // :273  G_xp = G x_p
   RET(sub_solve(p, true, p->g, p->t2));                   // :274  Finv_G_xp = F_inv @ G_xp
-  RET(v_axpby(p, 1.0, p->w, -1.0, p->t2, z, 4 * fs));     // :275  u = Finv_v - Finv_G_xp ; :276 concat
+  return 0;
+}
+// The apply is one CUDA graph (about 1800 kernel nodes at 4096^2) between a copy-in of v and the final combine:
+// every kernel inside works on plan-owned buffers, so its arguments never change and the graph is captured once.
+static int precond_apply(mpbp_plan* p, const double* v, double* z) {
+  const size_t fs = p->lev[0].fs();
+  CU(cudaMemcpyAsync(p->vin, v, 5 * fs * sizeof(double), cudaMemcpyDeviceToDevice, p->st));
+  p->pending_push = nullptr;
+  if (!p->use_graph) {
+    RET(precond_core(p));
+  } else {
+    if (!p->gexec_apply) {
+      const long long l0 = p->launches;
+      CU(cudaStreamBeginCapture(p->st, cudaStreamCaptureModeThreadLocal));
+      const int rc = precond_core(p);
+      cudaGraph_t g = nullptr;
+      const cudaError_t e = cudaStreamEndCapture(p->st, &g);
+      if (rc != 0) {
+        if (g) cudaGraphDestroy(g);
+        return rc;
+      }
+      CU(e);
+      CU(cudaGraphInstantiate(&p->gexec_apply, g, 0));
+      cudaGraphDestroy(g);
+      p->glaunches_apply = p->launches - l0;
+      p->launches = l0;
+    }
+    CU(cudaGraphLaunch(p->gexec_apply, p->st));
+    p->launches += p->glaunches_apply;
+    p->pending_push = nullptr;
+  }
+  // :275  u = Finv_v - Finv_G_xp ; :276  concat(u, x_p)
+  k_combine<<<ew_blocks(5 * fs), 256, 0, p->st>>>(p->w, p->t2, p->xp, z, 4 * fs, fs);
+  LAUNCH_CHECK(p);
   return 0;
 }
 
@@ -1128,6 +1246,7 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
       v.geo.pf = 3;  // measured best on B200 at 4096^2 (profiles/r1_tuning.txt)
       if (const char* e = getenv("MPBP_PF")) v.geo.pf = std::max(0, std::min(atoi(e), 64));
       if (const char* e = getenv("MPBP_RS")) v.geo.rs = std::max(1, std::min(atoi(e), v.rows));
+      if (!(v.rows & 1) && (v.geo.rs & 1)) v.geo.rs += 1;
       v.geoL = v.geo;
       {  // light kernels (16 resident blocks/SM): 32-row strips, halved until the grid has >= 4 blocks per SM
         int rs = 32;
@@ -1170,8 +1289,7 @@ extern "C" int mpbp_plan_destroy(mpbp_plan* p) {
   cudaDeviceSynchronize();
   // graphs first: captured NCCL collectives hold references on the communicator, and ncclCommDestroy
   // waits for them
-  for (int i = 0; i < 2; ++i)
-    if (p->gexec[i]) cudaGraphExecDestroy(p->gexec[i]);
+  if (p->gexec_apply) cudaGraphExecDestroy(p->gexec_apply);
   cudaDeviceSynchronize();
   if (p->comm_prev) cudaIpcCloseMemHandle(p->comm_prev);
   if (p->comm_next && p->comm_next != p->comm_prev) cudaIpcCloseMemHandle(p->comm_next);
@@ -1363,33 +1481,32 @@ extern "C" int mpbp_precond_apply_host(mpbp_plan* p, const double* v_host, doubl
 }
 
 // algorithmic bytes (SURVEY 8d accounting: every input read once, every output written once, one
-// coefficient field per stencil kernel) of one preconditioner apply under the current configuration
-static double vcycle_bytes(const mpbp_plan* p, int l, bool isF) {
+// coefficient field per stencil kernel) of one preconditioner apply under the current configuration.
+// Only the passes the fused kernels actually make are counted: no copies, no materialised V-cycle outputs.
+static double vcycle_bytes(const mpbp_plan* p, int l, bool isF, bool with_ep) {
   const mpbp_config& c = p->cfg;
   const int L = (int)p->lev.size();
   const double N = (double)p->lev[l].fs();
   if (l == L - 1) return 0.0;  // dense coarse solve: negligible
+  const Level& v = p->lev[l];
+  const bool even = !(v.rows & 1) && !(v.geo.rs & 1);
   double by = 0.0;
+  // the epilogue replaces the write of z (4N or N doubles) by read d, x + write d, x (upper bound: middle cycles)
+  const double ep_extra = with_ep ? (isF ? 4 : 1) * 8.0 * N * 3.0 : 0.0;
   if (isF) {
-    const bool fuse_pre = (p->fuse & 1) && !p->lev[l].dist && c.nu1 == 2 && p->lev[l].wdF != nullptr;
-    if (fuse_pre) {
-      by += 104 * N;                         // both pre-smoothing sweeps in one pass (reads b, omega/diag, theta)
-      by += c.nu2 * 104.0 * N;               // post-smoothing sweeps
-    } else {
-      by += 72 * N;                          // first sweep from x=0
-      by += (c.nu1 - 1 + c.nu2) * 104.0 * N; // Jacobi sweeps
-    }
-    by += 104 * N;                         // residual
-    by += 40 * N;                          // restrict (read 4N, write N)
-    by += 72 * N;                          // prolong + correct (read 4N + N, write 4N)
+    const bool fuse_pre = (p->fuse & 1) && !v.dist && c.nu1 == 2 && v.wdF != nullptr;
+    const bool fuse_rr = (p->fuse & 4) && !v.dist && even;
+    const bool fuse_post = (p->fuse & 2) && !v.dist && even && c.nu2 >= 1;
+    by += fuse_pre ? 104 * N : 72 * N + (c.nu1 - 1) * 104.0 * N;   // pre-smoothing (pair: reads b, omega/diag, theta)
+    by += fuse_rr ? 80 * N : (104 + 40) * N;                         // residual (+ restriction: writes N instead of 4N)
+    by += fuse_post ? 112 * N + (c.nu2 - 1) * 104.0 * N              // prolongation fused into the first post-sweep
+                    : 72 * N + c.nu2 * 104.0 * N;                    // x += P e ; nu2 sweeps
   } else {
-    by += 24 * N;
-    by += (c.nu1 - 1 + c.nu2) * 32.0 * N;
-    by += 32 * N;
-    by += 10 * N;
-    by += 18 * N;
+    by += 24 * N + (c.nu1 - 1) * 32.0 * N;
+    by += 32 * N + 10 * N;
+    by += 18 * N + c.nu2 * 32.0 * N;
   }
-  return by + vcycle_bytes(p, l + 1, isF);
+  return by + ep_extra + vcycle_bytes(p, l + 1, isF, false);
 }
 static double solve_bytes(const mpbp_plan* p, bool isF) {
   const mpbp_config& c = p->cfg;
@@ -1402,11 +1519,10 @@ static double solve_bytes(const mpbp_plan* p, bool isF) {
   } else {
     const int k = isF ? c.F_cycles : c.P_cycles;
     const double vec = isF ? 32 * N : 8 * N;  // one vector pass
-    by = k * vcycle_bytes(p, 0, isF);
+    by = k * vcycle_bytes(p, 0, isF, true);
+    by -= 2 * vec;                                            // first cycle reads neither d nor x
+    by -= (c.cheb ? 1 : 2 * k - 1) * vec;                     // last cycle does not write d (plain iteration: never d)
     by += (k - 1) * (isF ? 104 * N : 32 * N);                 // residual before every extra cycle
-    by += (k - 1) * (c.cheb ? 5 * vec : 3 * vec);             // x += z  / Chebyshev update
-    by += 2 * vec;                                            // rin = b (cycles run on fixed buffers)
-    by += c.cheb ? 4 * vec : 2 * vec;                         // d = z/theta ; x = d   /   x = z
   }
   if (!isF && c.project) by += 3 * 8 * N;
   return by;
@@ -1418,7 +1534,8 @@ extern "C" int mpbp_precond_bytes(const mpbp_plan* p, double* bytes) {
   by += 56 * N;             // K5  r = D w + v_p
   by += 48 * N + 72 * N + 48 * N;  // K7 -> K2 -> K5 chain for GtFG
   by += 48 * N;             // K7  G x_p
-  by += 96 * N;             // K8  w - y
+  by += 80 * N;             // copy-in of v (the graph's fixed input address)
+  by += 112 * N;            // K8  z = [w - y ; x_p]
   *bytes = by;
   return 0;
 }

@@ -146,6 +146,17 @@ __global__ void __launch_bounds__(256) k_halo_push(const double* __restrict__ x,
   }
 }
 
+// Chebyshev epilogue of the last smoothing sweep of a V-cycle: the sweep's result is the cycle's output z, which is
+// consumed in registers instead of being stored:  d = ca*d + cb*z ;  xk += d.
+struct ChebEp {
+  double ca, cb;     // d = ca*d + cb*z
+  double* d;         // Chebyshev direction (in/out)
+  double* xk;        // iterate (in/out)
+  int read_d;        // 0: first cycle (d = cb*z)
+  int read_x;        // 0: first cycle (xk = d)
+  int write_d;       // 0: last cycle (d is dead)
+};
+
 struct Geo {
   int n;     // columns (= global grid size of the level)
   int rows;  // local rows of the slab
@@ -214,7 +225,7 @@ __device__ __forceinline__ LaneGeom lane_geom(int n) {
   return g;
 }
 
-// Fused halo push (experimental, MPBP_PUSH_FUSED=1): the producing stencil kernel itself stores its first and
+// Fused halo push (MPBP_PUSH_FUSED): the producing stencil kernel itself stores its first and
 // last output rows into the ring neighbours' comm buffers (peer memory over NVLink) and the last block of each
 // edge strip releases that direction's flag -- the compute kernel IS the halo exchange, and because the edge
 // strips are scheduled first the transfer overlaps the interior of the slab.
@@ -226,390 +237,7 @@ struct PushOut {
   unsigned int* counters;     // [0] first-strip blocks done, [1] last-strip blocks done, [2] all edge blocks done
 };
 
-// ------------------------------------------------------------------------------------------
-// Velocity-block / full-system kernel.
-//   MODE 0: y = Op x            (Op = F, or A when WITH_P)         K1 / K2
-//   MODE 1: y = b - F x                                             K2 residual
-//   MODE 2: y = x + omega * (b - F x) / diag(F)                     K3, solve.py:149-159 (damped)
-// ------------------------------------------------------------------------------------------
-template <int MODE, bool WITH_P, bool PUSH>
-__device__ __forceinline__ void stokes_body(VecIn xin, const double* __restrict__ th, const double* __restrict__ b,
-                                            double* __restrict__ y, const Geo& g, const Phys& ph, double omega,
-                                            const PushOut& po) {
-  const LaneGeom lg = lane_geom(g.n);
-  if (!lg.alive) return;
-  const int n = g.n, rows = g.rows, c = lg.cc;
-  const int r0 = blockIdx.y * g.rs;
-  const int r1 = min(r0 + g.rs, rows);
-  if (r0 >= rows) return;
-  halo_wait(xin, r0 == 0, r1 == rows);
-  unsigned long long seq_out = 0ull;
-  double* push_prev = nullptr;  // neighbour's bot area: receives my row 0
-  double* push_next = nullptr;  // neighbour's top area: receives my row rows-1
-  if (PUSH) {
-    seq_out = *po.dseq + 1ull;  // bumped only after every edge block of this launch has finished
-    const int slot = (int)(seq_out & 1ull);
-    push_prev = comm_halo(po.prev_comm, po.area, slot, 1);
-    push_next = comm_halo(po.next_comm, po.area, slot, 0);
-  }
-
-  double sxf = 0.0, sxc = 0.0;
-  if (ph.mass_mode) {
-    sxf = ph.sxf[c];
-    sxc = ph.sxc[c];
-  }
-
-  // ---- prologue: rows r0-1 and r0 ----
-  double th_m = th_row(th, r0 - 1, n)[c];
-  double th_c = th_row(th, r0, n)[c];
-  double un_m = row_ptr(xin, 0, r0 - 1, rows, n)[c], vn_m = row_ptr(xin, 1, r0 - 1, rows, n)[c];
-  double us_m = row_ptr(xin, 2, r0 - 1, rows, n)[c], vs_m = row_ptr(xin, 3, r0 - 1, rows, n)[c];
-  double un_c = row_ptr(xin, 0, r0, rows, n)[c], vn_c = row_ptr(xin, 1, r0, rows, n)[c];
-  double us_c = row_ptr(xin, 2, r0, rows, n)[c], vs_c = row_ptr(xin, 3, r0, rows, n)[c];
-  double p_m = 0.0, p_c = 0.0;
-  if (WITH_P) {
-    p_m = row_ptr(xin, 4, r0 - 1, rows, n)[c];
-    p_c = row_ptr(xin, 4, r0, rows, n)[c];
-  }
-  const double a_m = th_m + shfl_up1(th_m);
-  double a_c = th_c + shfl_up1(th_c);
-  double node_c = 0.25 * (a_c + a_m);
-  double Tn_c = node_c * ((un_m - un_c) + (vn_c - shfl_up1(vn_c)));
-  double Ts_c = (1.0 - node_c) * ((us_m - us_c) + (vs_c - shfl_up1(vs_c)));
-  double Qn_m = th_m * ((shfl_dn1(un_m) - un_m) + (vn_c - vn_m));
-  double Qs_m = (1.0 - th_m) * ((shfl_dn1(us_m) - us_m) + (vs_c - vs_m));
-  double fv_c = 0.5 * (th_c + th_m);
-  double Vsum_c = vs_c + fv_c * (vn_c - vs_c);
-
-  // next row (r0+1) raw values, software-prefetched one row ahead of use
-  double th_p = th_row(th, r0 + 1, n)[c];
-  double un_p = row_ptr(xin, 0, r0 + 1, rows, n)[c], vn_p = row_ptr(xin, 1, r0 + 1, rows, n)[c];
-  double us_p = row_ptr(xin, 2, r0 + 1, rows, n)[c], vs_p = row_ptr(xin, 3, r0 + 1, rows, n)[c];
-  double p_p = 0.0;
-  if (WITH_P) p_p = row_ptr(xin, 4, r0 + 1, rows, n)[c];
-
-  const size_t fs = xin.fs;
-  const bool pfl = pf_lane();
-#pragma unroll 2
-  for (int r = r0; r < r1; ++r) {
-    // prefetch row r+2 (clamped to r1: the last prefetch is unused but stays in bounds of the halo)
-    const int rq = min(r + 2, r1);
-    const double th_q = th_row(th, rq, n)[c];
-    const double un_q = row_ptr(xin, 0, rq, rows, n)[c], vn_q = row_ptr(xin, 1, rq, rows, n)[c];
-    const double us_q = row_ptr(xin, 2, rq, rows, n)[c], vs_q = row_ptr(xin, 3, rq, rows, n)[c];
-    double p_q = 0.0;
-    if (WITH_P) p_q = row_ptr(xin, 4, rq, rows, n)[c];
-    double bn_u = 0.0, bn_v = 0.0, bs_u = 0.0, bs_v = 0.0;
-    const size_t off = (size_t)r * n + c;
-    if (g.pf > 0 && pfl) {
-      const int rp = r + g.pf;
-      if (rp <= r1) {
-        pf_l2(th_row(th, rp, n) + c);
-#pragma unroll
-        for (int k = 0; k < (WITH_P ? 5 : 4); ++k) pf_l2(row_ptr(xin, k, rp, rows, n) + c);
-        if (MODE != 0 && rp < r1) {
-          const size_t offp = (size_t)rp * n + c;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) pf_l2(b + offp + k * fs);
-        }
-      }
-    }
-    if (MODE != 0) {
-      bn_u = b[off];
-      bn_v = b[off + fs];
-      bs_u = b[off + 2 * fs];
-      bs_v = b[off + 3 * fs];
-    }
-
-    const double a_p = th_p + shfl_up1(th_p);
-    const double node_p = 0.25 * (a_p + a_c);
-    const double Tn_p = node_p * ((un_c - un_p) + (vn_p - shfl_up1(vn_p)));
-    const double Ts_p = (1.0 - node_p) * ((us_c - us_p) + (vs_p - shfl_up1(vs_p)));
-    const double Qn_c = th_c * ((shfl_dn1(un_c) - un_c) + (vn_p - vn_c));
-    const double Qs_c = (1.0 - th_c) * ((shfl_dn1(us_c) - us_c) + (vs_p - vs_c));
-    const double Lu_n = (Qn_c - shfl_up1(Qn_c)) + (Tn_c - Tn_p);
-    const double Lu_s = (Qs_c - shfl_up1(Qs_c)) + (Ts_c - Ts_p);
-    const double Lv_n = (shfl_dn1(Tn_c) - Tn_c) + (Qn_c - Qn_m);
-    const double Lv_s = (shfl_dn1(Ts_c) - Ts_c) + (Qs_c - Qs_m);
-
-    const double fu_c = 0.5 * a_c;
-    double mu, mv;
-    if (ph.mass_mode) {
-      const int gr = g.row0 + r;
-      mu = 0.25 * sxf * ph.syc[gr] + 0.5;  // thn(-(r+1/2)h, c h), preconditioner.py:325
-      mv = 0.25 * sxc * ph.syf[gr] + 0.5;  // thn(-r h, (c+1/2)h), preconditioner.py:326
-    } else {
-      mu = fu_c;
-      mv = fv_c;
-    }
-    const double dXu = ph.d_u * (ph.xi * fu_c * (1.0 - fu_c));  // preconditioner.py:124
-    const double dXv = ph.d_u * (ph.xi * fv_c * (1.0 - fv_c));  // preconditioner.py:125
-    const double du = un_c - us_c, dv = vn_c - vs_c;
-    const double cmu = ph.c * mu, cmv = ph.c * mv;
-    double y_un = cmu * un_c - dXu * du + ph.kap_n * Lu_n;
-    double y_us = (ph.c - cmu) * us_c + dXu * du + ph.kap_s * Lu_s;
-    double y_vn = cmv * vn_c - dXv * dv + ph.kap_n * Lv_n;
-    double y_vs = (ph.c - cmv) * vs_c + dXv * dv + ph.kap_s * Lv_s;
-    const double fv_p = 0.5 * (th_p + th_c);
-    const double Vsum_p = vs_p + fv_p * (vn_p - vs_p);
-    double y_p = 0.0;
-    if (WITH_P) {
-      const double gx = ph.dp_h * (p_c - shfl_up1(p_c));  // preconditioner.py:204-210
-      const double gy = ph.dp_h * (p_m - p_c);            // preconditioner.py:213-219
-      y_un += fu_c * gx;
-      y_us += (1.0 - fu_c) * gx;
-      y_vn += fv_c * gy;
-      y_vs += (1.0 - fv_c) * gy;
-      const double Usum_c = us_c + fu_c * du;
-      y_p = ph.ddiv_h * ((shfl_dn1(Usum_c) - Usum_c) + (Vsum_c - Vsum_p));  // preconditioner.py:221-238, :312
-    }
-    if (MODE == 1) {
-      y_un = bn_u - y_un;
-      y_vn = bn_v - y_vn;
-      y_us = bs_u - y_us;
-      y_vs = bs_v - y_vs;
-    }
-    if (MODE == 2) {
-      const double node_e = shfl_dn1(node_c);
-      const double su = a_c + node_c + node_p;           // tE+tW+nN+nS, preconditioner.py:127
-      const double sv = th_m + th_c + node_c + node_e;   // tN+tC+nL+nR, preconditioner.py:242
-      const double d_un = cmu - dXu - ph.kap_n * su;
-      const double d_us = (ph.c - cmu) - dXu - ph.kap_s * (4.0 - su);
-      const double d_vn = cmv - dXv - ph.kap_n * sv;
-      const double d_vs = (ph.c - cmv) - dXv - ph.kap_s * (4.0 - sv);
-      y_un = un_c + omega * (bn_u - y_un) * fast_rcp(d_un);
-      y_us = us_c + omega * (bs_u - y_us) * fast_rcp(d_us);
-      y_vn = vn_c + omega * (bn_v - y_vn) * fast_rcp(d_vn);
-      y_vs = vs_c + omega * (bs_v - y_vs) * fast_rcp(d_vs);
-    }
-    if (lg.store) {
-      y[off] = y_un;
-      y[off + fs] = y_vn;
-      y[off + 2 * fs] = y_us;
-      y[off + 3 * fs] = y_vs;
-      if (WITH_P && MODE == 0) y[off + 4 * fs] = y_p;
-      if (PUSH) {
-        if (r == 0) {
-          push_prev[c] = y_un;
-          push_prev[n + c] = y_vn;
-          push_prev[2 * n + c] = y_us;
-          push_prev[3 * n + c] = y_vs;
-        }
-        if (r == rows - 1) {
-          push_next[c] = y_un;
-          push_next[n + c] = y_vn;
-          push_next[2 * n + c] = y_us;
-          push_next[3 * n + c] = y_vs;
-        }
-      }
-    }
-    // rotate the window
-    th_m = th_c; th_c = th_p; th_p = th_q;
-    a_c = a_p; node_c = node_p;
-    un_c = un_p; vn_c = vn_p; us_c = us_p; vs_c = vs_p;
-    un_p = un_q; vn_p = vn_q; us_p = us_q; vs_p = vs_q;
-    p_m = p_c; p_c = p_p; p_p = p_q;
-    Tn_c = Tn_p; Ts_c = Ts_p; Qn_m = Qn_c; Qs_m = Qs_c;
-    fv_c = fv_p; Vsum_c = Vsum_p;
-  }
-  if (PUSH) {
-    const bool first = (r0 == 0), last = (r1 == rows);
-    if (first || last) {
-      __threadfence_system();
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        const unsigned int gx = gridDim.x;
-        const int slot = (int)(seq_out & 1ull);
-        if (first && atomicAdd(&po.counters[0], 1u) == gx - 1) {
-          po.counters[0] = 0u;
-          __threadfence_system();
-          st_release_sys(comm_flag(po.prev_comm, slot, 1), seq_out);
-        }
-        if (last && atomicAdd(&po.counters[1], 1u) == gx - 1) {
-          po.counters[1] = 0u;
-          __threadfence_system();
-          st_release_sys(comm_flag(po.next_comm, slot, 0), seq_out);
-        }
-        const unsigned int total = gx * ((gridDim.y == 1) ? 1u : 2u);
-        if (atomicAdd(&po.counters[2], 1u) == total - 1) {
-          po.counters[2] = 0u;
-          *po.dseq = seq_out;
-        }
-      }
-    }
-  }
-}
-
-template <int MODE, bool WITH_P, int MINB = 0>
-__global__ void __launch_bounds__(kBlockThreads, MINB) k_stokes(VecIn xin, const double* __restrict__ th,
-                                                          const double* __restrict__ b, double* __restrict__ y,
-                                                          Geo g, Phys ph, double omega) {
-  const PushOut po{};
-  stokes_body<MODE, WITH_P, false>(xin, th, b, y, g, ph, omega, po);
-}
-
-// same arithmetic, output rows 0 and rows-1 additionally pushed to the ring neighbours (see PushOut)
-template <int MODE>
-__global__ void __launch_bounds__(kBlockThreads, 5) k_stokes_push(VecIn xin, const double* __restrict__ th,
-                                                               const double* __restrict__ b, double* __restrict__ y,
-                                                               Geo g, Phys ph, double omega, PushOut po) {
-  stokes_body<MODE, false, true>(xin, th, b, y, g, ph, omega, po);
-}
-
-// ------------------------------------------------------------------------------------------
-// Fused smoothing kernels for whole-grid (non slab-distributed) levels.  Same marching structure as
-// k_stokes<2,false>; the difference is how a value of the iterate enters the register window:
-//   V = 0  pre-smoothing pair from a zero guess in ONE pass:  x1 = wd * b (wd = omega/diag(F), precomputed),
-//          x2 = x1 + wd * (b - F x1).  Replaces k_jacobi0_F + one k_stokes<2,false> sweep: reads b, wd, theta
-//          and writes x2 (104N B) instead of 72N + 104N B.
-//   V = 1  coarse-grid correction + first post-smoothing sweep in ONE pass:  xt = x + P e_c (P = 4 R^T),
-//          x_new = xt + omega (b - F xt)/diag.  Replaces k_prolong_add_F (72N B) + one sweep.
-// ------------------------------------------------------------------------------------------
-struct FuseArgs {
-  VecIn wd;          // V = 0: omega / diag(F), 4 fields, viewed with the same periodic wrap as the rhs
-  const double* ec;  // V = 1: coarse correction, 4 fields of nc x nc
-  int nc;
-};
-
-template <int V>
-__global__ void __launch_bounds__(kBlockThreads, V == 0 ? 5 : 4) k_stokes_fused(VecIn xin, const double* __restrict__ th,
-                                                                const double* __restrict__ b, double* __restrict__ y,
-                                                                Geo g, Phys ph, double omega, FuseArgs fa) {
-  const LaneGeom lg = lane_geom(g.n);
-  if (!lg.alive) return;
-  const int n = g.n, rows = g.rows, c = lg.cc;
-  const int r0 = blockIdx.y * g.rs;
-  const int r1 = min(r0 + g.rs, rows);
-  if (r0 >= rows) return;
-  const int nc = fa.nc;
-  const int C = c >> 1, Cp = (C + 1 == nc) ? 0 : C + 1;
-  const bool codd = (c & 1) != 0;
-
-  auto ldx = [&](int k, int row) -> double {
-    const double raw = row_ptr(xin, k, row, rows, n)[c];
-    if (V == 0) return raw * row_ptr(fa.wd, k, row, rows, n)[c];
-    const int fr = row < 0 ? row + rows : (row >= rows ? row - rows : row);  // whole grid on this rank: periodic
-    const int R = fr >> 1;
-    const double* e = fa.ec + (size_t)k * nc * nc;
-    double pe;
-    if ((k & 1) == 0) {  // u-type field: linear in x, constant in y
-      const double* er = e + (size_t)R * nc;
-      pe = codd ? 0.5 * (er[C] + er[Cp]) : er[C];
-    } else {             // v-type field: linear in y, constant in x
-      pe = e[(size_t)R * nc + C];
-      if (fr & 1) {
-        const int Rp = (R + 1 == nc) ? 0 : R + 1;
-        pe = 0.5 * (pe + e[(size_t)Rp * nc + C]);
-      }
-    }
-    return raw + pe;
-  };
-
-  double sxf = 0.0, sxc = 0.0;
-  if (ph.mass_mode) {
-    sxf = ph.sxf[c];
-    sxc = ph.sxc[c];
-  }
-  double th_m = th_row(th, r0 - 1, n)[c];
-  double th_c = th_row(th, r0, n)[c];
-  double un_m = ldx(0, r0 - 1), vn_m = ldx(1, r0 - 1), us_m = ldx(2, r0 - 1), vs_m = ldx(3, r0 - 1);
-  double un_c = ldx(0, r0), vn_c = ldx(1, r0), us_c = ldx(2, r0), vs_c = ldx(3, r0);
-  const double a_m = th_m + shfl_up1(th_m);
-  double a_c = th_c + shfl_up1(th_c);
-  double node_c = 0.25 * (a_c + a_m);
-  double Tn_c = node_c * ((un_m - un_c) + (vn_c - shfl_up1(vn_c)));
-  double Ts_c = (1.0 - node_c) * ((us_m - us_c) + (vs_c - shfl_up1(vs_c)));
-  double Qn_m = th_m * ((shfl_dn1(un_m) - un_m) + (vn_c - vn_m));
-  double Qs_m = (1.0 - th_m) * ((shfl_dn1(us_m) - us_m) + (vs_c - vs_m));
-  double fv_c = 0.5 * (th_c + th_m);
-  double th_p = th_row(th, r0 + 1, n)[c];
-  double un_p = ldx(0, r0 + 1), vn_p = ldx(1, r0 + 1), us_p = ldx(2, r0 + 1), vs_p = ldx(3, r0 + 1);
-
-  const size_t fs = xin.fs;
-  const bool pfl = pf_lane();
-#pragma unroll 2
-  for (int r = r0; r < r1; ++r) {
-    const int rq = min(r + 2, r1);
-    const double th_q = th_row(th, rq, n)[c];
-    const double un_q = ldx(0, rq), vn_q = ldx(1, rq), us_q = ldx(2, rq), vs_q = ldx(3, rq);
-    const size_t off = (size_t)r * n + c;
-    if (g.pf > 0 && pfl) {
-      const int rp = r + g.pf;
-      if (rp <= r1) {
-        pf_l2(th_row(th, rp, n) + c);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          pf_l2(row_ptr(xin, k, rp, rows, n) + c);
-          if (V == 0) pf_l2(row_ptr(fa.wd, k, rp, rows, n) + c);
-        }
-        if (V == 1 && rp < r1) {
-          const size_t offp = (size_t)rp * n + c;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) pf_l2(b + offp + k * fs);
-        }
-      }
-    }
-    const double bn_u = b[off], bn_v = b[off + fs], bs_u = b[off + 2 * fs], bs_v = b[off + 3 * fs];
-
-    const double a_p = th_p + shfl_up1(th_p);
-    const double node_p = 0.25 * (a_p + a_c);
-    const double Tn_p = node_p * ((un_c - un_p) + (vn_p - shfl_up1(vn_p)));
-    const double Ts_p = (1.0 - node_p) * ((us_c - us_p) + (vs_p - shfl_up1(vs_p)));
-    const double Qn_c = th_c * ((shfl_dn1(un_c) - un_c) + (vn_p - vn_c));
-    const double Qs_c = (1.0 - th_c) * ((shfl_dn1(us_c) - us_c) + (vs_p - vs_c));
-    const double Lu_n = (Qn_c - shfl_up1(Qn_c)) + (Tn_c - Tn_p);
-    const double Lu_s = (Qs_c - shfl_up1(Qs_c)) + (Ts_c - Ts_p);
-    const double Lv_n = (shfl_dn1(Tn_c) - Tn_c) + (Qn_c - Qn_m);
-    const double Lv_s = (shfl_dn1(Ts_c) - Ts_c) + (Qs_c - Qs_m);
-
-    const double fu_c = 0.5 * a_c;
-    double mu, mv;
-    if (ph.mass_mode) {
-      const int gr = g.row0 + r;
-      mu = 0.25 * sxf * ph.syc[gr] + 0.5;
-      mv = 0.25 * sxc * ph.syf[gr] + 0.5;
-    } else {
-      mu = fu_c;
-      mv = fv_c;
-    }
-    const double dXu = ph.d_u * (ph.xi * fu_c * (1.0 - fu_c));
-    const double dXv = ph.d_u * (ph.xi * fv_c * (1.0 - fv_c));
-    const double du = un_c - us_c, dv = vn_c - vs_c;
-    const double cmu = ph.c * mu, cmv = ph.c * mv;
-    const double F_un = cmu * un_c - dXu * du + ph.kap_n * Lu_n;
-    const double F_us = (ph.c - cmu) * us_c + dXu * du + ph.kap_s * Lu_s;
-    const double F_vn = cmv * vn_c - dXv * dv + ph.kap_n * Lv_n;
-    const double F_vs = (ph.c - cmv) * vs_c + dXv * dv + ph.kap_s * Lv_s;
-    double y_un, y_vn, y_us, y_vs;
-    if (V == 0) {
-      const double* wd = fa.wd.x + off;
-      y_un = un_c + (bn_u - F_un) * wd[0];
-      y_vn = vn_c + (bn_v - F_vn) * wd[fs];
-      y_us = us_c + (bs_u - F_us) * wd[2 * fs];
-      y_vs = vs_c + (bs_v - F_vs) * wd[3 * fs];
-    } else {
-      const double node_e = shfl_dn1(node_c);
-      const double su = a_c + node_c + node_p;
-      const double sv = th_m + th_c + node_c + node_e;
-      y_un = un_c + omega * (bn_u - F_un) * fast_rcp(cmu - dXu - ph.kap_n * su);
-      y_us = us_c + omega * (bs_u - F_us) * fast_rcp((ph.c - cmu) - dXu - ph.kap_s * (4.0 - su));
-      y_vn = vn_c + omega * (bn_v - F_vn) * fast_rcp(cmv - dXv - ph.kap_n * sv);
-      y_vs = vs_c + omega * (bs_v - F_vs) * fast_rcp((ph.c - cmv) - dXv - ph.kap_s * (4.0 - sv));
-    }
-    if (lg.store) {
-      y[off] = y_un;
-      y[off + fs] = y_vn;
-      y[off + 2 * fs] = y_us;
-      y[off + 3 * fs] = y_vs;
-    }
-    th_m = th_c; th_c = th_p; th_p = th_q;
-    a_c = a_p; node_c = node_p;
-    un_c = un_p; vn_c = vn_p; us_c = us_p; vs_c = vs_p;
-    un_p = un_q; vn_p = vn_q; us_p = us_q; vs_p = vs_q;
-    Tn_c = Tn_p; Ts_c = Ts_p; Qn_m = Qn_c; Qs_m = Qs_c;
-    fv_c = 0.5 * (th_c + th_m);
-  }
-}
+// (the velocity-block / full-system marching kernel with its fused variants lives in stokes.cuh)
 
 __global__ void k_fill(double* __restrict__ x, double v, size_t len) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -685,10 +313,11 @@ __global__ void __launch_bounds__(kBlockThreads) k_jacobi0_F(const double* __res
 // Pressure-Poisson operator GtG = -D G (solve.py:246-247): 5-point, face weights wu = fu_n^2+fu_s^2.
 //   MODE 0: y = GtG p ; 1: y = b - GtG p ; 2: y = p + omega (b - GtG p)/diag ; 3: y = omega b/diag
 // ------------------------------------------------------------------------------------------
-template <int MODE>
+//   CHEB (MODE 2): the sweep's result z goes through the Chebyshev epilogue (ChebEp) instead of being stored
+template <int MODE, bool CHEB = false>
 __global__ void __launch_bounds__(kBlockThreads) k_poisson(VecIn pin, const double* __restrict__ th,
                                                            const double* __restrict__ b, double* __restrict__ y,
-                                                           Geo g, Phys ph, double omega) {
+                                                           Geo g, Phys ph, double omega, ChebEp ce = ChebEp{}) {
   const LaneGeom lg = lane_geom(g.n);
   if (!lg.alive) return;
   const int n = g.n, rows = g.rows, c = lg.cc;
@@ -726,7 +355,16 @@ __global__ void __launch_bounds__(kBlockThreads) k_poisson(VecIn pin, const doub
       if (MODE == 2) out = p_c + omega * (b[off] - out) * rinv;
       else out = omega * b[off] * rinv;
     }
-    if (lg.store) y[off] = out;
+    if (lg.store) {
+      if (CHEB) {
+        const double dk = ce.read_d ? ce.d[off] : 0.0;
+        const double dn = ce.ca * dk + ce.cb * out;
+        if (ce.write_d) ce.d[off] = dn;
+        ce.xk[off] = (ce.read_x ? ce.xk[off] : 0.0) + dn;
+      } else {
+        y[off] = out;
+      }
+    }
     th_m = th_c; th_c = th_p; p_m = p_c; p_c = p_p; wv_c = wv_p; Hy_c = Hy_p;
   }
 }

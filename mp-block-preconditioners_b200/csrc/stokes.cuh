@@ -22,15 +22,6 @@
 
 namespace mpbp {
 
-struct ChebEp {
-  double ca, cb;     // d = ca*d + cb*z
-  double* d;         // Chebyshev direction (in/out)
-  double* xk;        // iterate (in/out)
-  int read_d;        // 0: first cycle (d = cb*z)
-  int read_x;        // 0: first cycle (xk = d)
-  int write_d;       // 0: last cycle (d is dead)
-};
-
 struct StokesArgs {
   VecIn xin;                 // input view (IN 1: the view of b)
   const double* th;          // padded theta
@@ -320,10 +311,14 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
         d2 = a.ce.ca * d2 + a.ce.cb * y_us;
         d3 = a.ce.ca * d3 + a.ce.cb * y_vs;
         if (a.ce.write_d) { d[o0] = d0; d[o1] = d1; d[o2] = d2; d[o3] = d3; }
-        xk[o0] = x0 + d0;
-        xk[o1] = x1 + d1;
-        xk[o2] = x2 + d2;
-        xk[o3] = x3 + d3;
+        y_un = x0 + d0;  // (the iterate is what a fused halo push sends on)
+        y_vn = x1 + d1;
+        y_us = x2 + d2;
+        y_vs = x3 + d3;
+        xk[o0] = y_un;
+        xk[o1] = y_vn;
+        xk[o2] = y_us;
+        xk[o3] = y_vs;
       }
     } else {
       // EP 2: full weighting onto the coarse grid (k_restrict_F's weights): u: (1/4,1/2,1/4) over columns x (1/2,1/2)

@@ -11,10 +11,15 @@ import torch
 import mp_block_preconditioners_b200 as mp
 from mp_block_preconditioners_b200.utils import device_norms, manufactured_device
 
-CONFIGS = [(512, 1.0, 4, 2), (2048, 1.0e3, 4, 2), (4096, 1.0e4, 4, 2), (4096, 1.0e4, 6, 2)]
+# (n, eta_n, F cycles, GtG cycles, Chebyshev interval)
+CONFIGS = [(512, 1.0, 6, 2, (0.75, 1.2)), (2048, 1.0e3, 6, 2, (0.75, 1.2)), (4096, 1.0e4, 6, 2, (0.75, 1.2)),
+           (4096, 1.0e4, 5, 2, (0.75, 1.2)), (4096, 1.0e4, 5, 2, (0.78, 1.17)), (4096, 1.0e4, 6, 2, (0.78, 1.17)),
+           (2048, 1.0e4, 6, 2, (0.75, 1.2)), (1024, 1.0e4, 6, 2, (0.75, 1.2))]
+if len(sys.argv) > 1:
+    CONFIGS = [c for c in CONFIGS if c[0] <= int(sys.argv[1])]
 out = []
-for n, eta_n, kF, kP in CONFIGS:
-    sub = mp.SubSolver(kind="mg", F_cycles=kF, P_cycles=kP, cheb=True)
+for n, eta_n, kF, kP, (lmin, lmax) in CONFIGS:
+    sub = mp.SubSolver(kind="mg", F_cycles=kF, P_cycles=kP, cheb=True, lmin=lmin, lmax=lmax)
     bp = mp.MultiphaseBlockPreconditioner(n, 1.0, eta_n, 1.0, sub_solver=sub)
     A = bp.get_big_A_matrix(1.0, -1.0)[0]
     M = bp.approx_schur_operator(1.0, -1.0)
@@ -27,12 +32,12 @@ for n, eta_n, kF, kP in CONFIGS:
     hist = mp.fgmres.last_history
     true_rel = float(torch.linalg.norm(b - A @ x) / torch.linalg.norm(b))
     L1, L2, mx = device_norms(A.plan, x, u, (1.0 / n) ** 2)
-    rec = dict(n=n, eta_n=eta_n, F_cycles=kF, P_cycles=kP, restart=40, info=info, iterations=len(hist), seconds=dt,
+    rec = dict(n=n, eta_n=eta_n, F_cycles=kF, P_cycles=kP, interval=[lmin, lmax], restart=40, info=info, iterations=len(hist), seconds=dt,
                its_per_s=len(hist) / dt, true_rel_residual=true_rel, err_L1=L1, err_L2=L2, err_max=mx,
                history=[float(h) for h in hist])
     out.append(rec)
     print({k: v for k, v in rec.items() if k != "history"}, flush=True)
-    bp.close()
+    A.plan.close()
     del A, M, u, b, x, bp
     torch.cuda.empty_cache()
 json.dump(out, open("gpurun_out/solve_configs.json", "w"), indent=1)

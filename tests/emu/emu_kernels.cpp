@@ -50,11 +50,13 @@ void emu_stokes(int mode, int with_p, int n, const double* prm, int mass_mode, c
   const Phys ph = make_phys(n, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], prm[6], mass_mode, t);
   const Geo g{n, n, 0, rs, pf};
   const VecIn in = whole_grid_view(x, n);
+  StokesArgs a{};
+  a.xin = in; a.th = th_pad; a.b = b; a.y = y; a.g = g; a.ph = ph; a.omega = omega;
   emu::launch(sgrid(n, rs), dim3(kBlockThreads), [&] {
-    if (with_p) k_stokes<0, true>(in, th_pad, b, y, g, ph, omega);
-    else if (mode == 0) k_stokes<0, false>(in, th_pad, b, y, g, ph, omega);
-    else if (mode == 1) k_stokes<1, false>(in, th_pad, b, y, g, ph, omega);
-    else k_stokes<2, false>(in, th_pad, b, y, g, ph, omega);
+    if (with_p) k_stokes_x<0, 0, true, 0, false, 0>(a);
+    else if (mode == 0) k_stokes_x<0, 0, false, 0, false, 0>(a);
+    else if (mode == 1) k_stokes_x<0, 1, false, 0, false, 0>(a);
+    else k_stokes_x<0, 2, false, 0, false, 0>(a);
   });
 }
 
@@ -64,13 +66,15 @@ void emu_stokes_fused(int variant, int n, const double* prm, int mass_mode, cons
   const Phys ph = make_phys(n, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], prm[6], mass_mode, t);
   const Geo g{n, n, 0, rs, pf};
   const VecIn in = whole_grid_view(x, n);
-  FuseArgs fa{};
-  if (wd) fa.wd = whole_grid_view(wd, n);
-  fa.ec = ec;
-  fa.nc = n / 2;
+  StokesArgs a{};
+  a.xin = in; a.th = th_pad; a.b = b; a.y = y; a.g = g; a.ph = ph; a.omega = omega;
+  if (wd) a.wd = whole_grid_view(wd, n);
+  if (ec) a.cin = whole_grid_view(ec, n / 2);
+  a.nc = n / 2;
+  a.rows_c = n / 2;
   emu::launch(sgrid(n, rs), dim3(kBlockThreads), [&] {
-    if (variant == 0) k_stokes_fused<0>(in, th_pad, b, y, g, ph, omega, fa);
-    else k_stokes_fused<1>(in, th_pad, b, y, g, ph, omega, fa);
+    if (variant == 0) k_stokes_x<1, 2, false, 0, false, 0>(a);
+    else k_stokes_x<2, 2, false, 0, false, 0>(a);
   });
 }
 
@@ -262,8 +266,10 @@ void emu_slab_apply_A(int P, int rounds, int n, const double* prm, const double*
       in.dseq = &dseq[g];
       in.comm = comm[g].data();
       in.area = area;
+      StokesArgs a{};
+      a.xin = in; a.th = thp[g].data(); a.y = ys[g].data(); a.g = geo; a.ph = ph;
       emu::launch(dim3((n + kWarpCols * kBlockWarps - 1) / (kWarpCols * kBlockWarps), (rows + rs - 1) / rs),
-                  dim3(kBlockThreads), [&] { k_stokes<0, true>(in, thp[g].data(), nullptr, ys[g].data(), geo, ph, 0.0); });
+                  dim3(kBlockThreads), [&] { k_stokes_x<0, 0, true, 0, false, 0>(a); });
     }
   }
   for (int g = 0; g < P; ++g)
@@ -320,11 +326,13 @@ void emu_slab_fused_push_chain(int P, int n, const double* prm, const double* th
       const Geo geo{n, rows, g * rows, rs, 3};
       const double* src = (step == 1) ? xb[g].data() : xa[g].data();
       double* dst = (step == 1) ? xa[g].data() : xb[g].data();
-      const VecIn in = view(g, src);
-      const PushOut po{comm[prev].data(), comm[next].data(), area, &dseq[g], &counter[g][4]};
+      StokesArgs a{};
+      a.xin = view(g, src);
+      a.th = thp[g].data(); a.b = bs[g].data(); a.y = dst; a.g = geo; a.ph = ph; a.omega = omega;
+      a.po = PushOut{comm[prev].data(), comm[next].data(), area, &dseq[g], &counter[g][4]};
       emu::launch(grid, dim3(kBlockThreads), [&] {
-        if (step < 2) k_stokes_push<2>(in, thp[g].data(), bs[g].data(), dst, geo, ph, omega, po);
-        else k_stokes<1, false>(in, thp[g].data(), bs[g].data(), dst, geo, ph, omega);
+        if (step < 2) k_stokes_x<0, 2, false, 0, true, 0>(a);
+        else k_stokes_x<0, 1, false, 0, false, 0>(a);
       });
     }
   }
