@@ -365,13 +365,18 @@ def run_parity(mp, p, A, M, b_dev, z, n, w, sub, rank, world):
 
         def nrel(a, b_):
             return float(np.abs(a - b_).max() / np.abs(b_).max())
+        zb = co.precond(b)
+        # the smooth manufactured rhs is an ill-conditioned input of M (BFBt amplifies rounding in the rough modes by
+        # ~eta_n/h^2 relative to the smooth content): the oracle's own M b moves by `sens` under 1-ulp perturbations
+        sens = max(nrel(co.precond(b * (1.0 + 1.2e-16 * rng.standard_normal(b.shape))), zb) for _ in range(3))
         out = {"against": "C oracle (oracle/mpbp_oracle_c.c), 1024^2, benchmarked contrast and sub-solver",
                "apply_A_relerr": nrel(Am @ v, co.apply_A(v)),
                "precond_apply_relerr": nrel(Mm @ v, co.precond(v)),
-               "precond_apply_rhs_relerr": nrel(Mm @ b, co.precond(b)),
-               "tolerance": {"apply_A": 1e-13, "precond_apply": 1e-9}}
+               "precond_apply_rhs_relerr": nrel(Mm @ b, zb),
+               "precond_apply_rhs_oracle_sensitivity_1ulp": sens,
+               "tolerance": {"apply_A": 1e-13, "precond_apply": 1e-9, "precond_apply_rhs": "max(1e-9, 10 x sensitivity)"}}
         out["ok"] = bool(out["apply_A_relerr"] < 1e-13 and out["precond_apply_relerr"] < 1e-9
-                         and out["precond_apply_rhs_relerr"] < 1e-9)
+                         and out["precond_apply_rhs_relerr"] < max(1e-9, 10.0 * sens))
         Am.plan.close()
         return out
     from mp_block_preconditioners_b200.parallel import scatter_slab

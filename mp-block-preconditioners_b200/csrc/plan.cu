@@ -282,7 +282,7 @@ static int halo_exchange(mpbp_plan* p, Level& v, const double* x, int nf, size_t
     // push my boundary rows straight into the neighbours' halo areas (dir 0 = top, 1 = bot) and release
     // their flags; consumers wait on the flags inside the stencil kernel (edge strips only)
     k_halo_push<<<(nf * v.n + 255) / 256, 256, 0, p->st>>>(x, nf, fs, v.rows, v.n, p->comm_prev, p->comm_next,
-                                                           p->comm_area, p->dseq, p->counter + 32);
+                                                           p->comm_local, p->comm_area, p->dseq, p->counter + 32);
     p->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -353,7 +353,7 @@ static int launch_sx(mpbp_plan* p, int l, SxKind k, StokesArgs& a) {
   if ((k.in == 2 || k.ep == 2) && ((v.rows & 1) || (v.geo.rs & 1) || v.dist))
     return set_err(MPBP_E_STATE, "internal: row-pair kernel on an odd / distributed level (rows %d, rs %d)", v.rows, v.geo.rs);
   const dim3 grid((unsigned)((v.n + wc * kBlockWarps - 1) / (wc * kBlockWarps)), (unsigned)((v.rows + v.geo.rs - 1) / v.geo.rs));
-  if (k.push) a.po = PushOut{p->comm_prev, p->comm_next, p->comm_area, p->dseq, p->counter + 40};
+  if (k.push) a.po = PushOut{p->comm_prev, p->comm_next, p->comm_local, p->comm_area, p->dseq, p->counter + 40};
   const int key = k.in * 10000 + k.mode * 1000 + (k.with_p ? 100 : 0) + k.ep * 10 + (k.push ? 1 : 0);
   switch (key) {
     case 100: sx_launch<0, 0, true, 0, false, 5>(p, grid, a); break;    // y = A x

@@ -93,12 +93,27 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 #endif
-// warp-level wait for the neighbours' halo rows (called by whole warps; lane 0 polls).
-// Slot-reuse invariant (two slots, sequence s lives in slot s&1): a rank's push s+2 overwrites the slot its
-// neighbours read for sequence s, so it must be ordered after BOTH neighbours' consumers of sequence s.  That
-// holds only if every consumer kernel of sequence s+1 on this rank acquires BOTH neighbours' flags (each
-// neighbour's push s+1 is stream-ordered after its own consumer of s).  Hence every halo consumer calls this
-// with need_top on its first strip and need_bot on its last strip, even when it reads one side only.
+// Halo protocol.  Exchange number s (identical on all ranks: every rank runs the same kernel sequence) lives in
+// slot s&1 of the receiver's comm buffer; the receiver's flag (slot, dir) holds the newest sequence the neighbour
+// on that side has fully written.  Two rules make slot reuse safe for any number of ranks:
+//  * consumer: a kernel reading exchange s waits (edge strips only) until flag(s&1, dir) >= s;
+//  * producer (credit): before writing exchange q into neighbour X's slot q&1 -- which still holds q-2 -- the
+//    producer waits until X's flag for q-1 has arrived HERE.  X released that flag from a kernel that is
+//    stream-ordered after every kernel of X that read q-2 (at most one exchange is outstanding), so X is done
+//    with the slot.  No cycle: X's push q-1 itself only needs this rank's q-2, sent long ago.
+// The credit makes the protocol independent of which sides a consumer happens to read, and of pushes that are
+// never consumed (a fused push whose result the next kernel does not need).
+__device__ __forceinline__ void halo_credit(char* my_comm, unsigned long long q, bool to_prev, bool to_next) {
+  if (q < 2ull) return;
+  const int slot = (int)((q - 1ull) & 1ull);
+  if (to_prev)
+    while (ld_acquire_sys(comm_flag(my_comm, slot, 0)) < q - 1ull) {
+    }
+  if (to_next)
+    while (ld_acquire_sys(comm_flag(my_comm, slot, 1)) < q - 1ull) {
+    }
+}
+// warp-level wait for the neighbours' halo rows (called by whole warps; lane 0 polls)
 __device__ __forceinline__ void halo_wait(VecIn& v, bool need_top, bool need_bot) {
   if (v.dseq == nullptr) return;
   resolve_halo(v);
@@ -118,10 +133,12 @@ __device__ __forceinline__ void halo_wait(VecIn& v, bool need_top, bool need_bot
 // the last block to finish publishes the flags.  Replaces an ncclSend/ncclRecv pair per field and
 // direction.
 __global__ void __launch_bounds__(256) k_halo_push(const double* __restrict__ x, int nf, size_t fs, int rows, int n,
-                                                   char* prev_comm, char* next_comm, size_t area,
+                                                   char* prev_comm, char* next_comm, char* my_comm, size_t area,
                                                    unsigned long long* dseq, unsigned int* done_counter) {
   const unsigned long long seq = *dseq + 1ull;  // read before this block's ticket, written only by the last block
   const int slot = (int)(seq & 1ull);
+  if (threadIdx.x == 0) halo_credit(my_comm, seq, true, true);
+  __syncthreads();
   double* __restrict__ prev_bot = comm_halo(prev_comm, area, slot, 1);
   double* __restrict__ next_top = comm_halo(next_comm, area, slot, 0);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -232,6 +249,7 @@ __device__ __forceinline__ LaneGeom lane_geom(int n) {
 struct PushOut {
   char* prev_comm;            // neighbours' comm buffers (mapped peer memory)
   char* next_comm;
+  char* my_comm;              // this rank's comm buffer (credit flags)
   size_t area;                // doubles per (slot, direction) halo area
   unsigned long long* dseq;   // this rank's exchange counter: output rows go out under sequence *dseq + 1
   unsigned int* counters;     // [0] first-strip blocks done, [1] last-strip blocks done, [2] all edge blocks done

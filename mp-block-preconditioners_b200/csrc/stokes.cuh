@@ -78,6 +78,10 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
     const int slot = (int)(seq_out & 1ull);
     push_prev = comm_halo(a.po.prev_comm, a.po.area, slot, 1);
     push_next = comm_halo(a.po.next_comm, a.po.area, slot, 0);
+    if (EDGE && (r0 == 0 || r1 == rows)) {
+      if (lane == 0) halo_credit(a.po.my_comm, seq_out, r0 == 0, r1 == rows);
+      __syncwarp();
+    }
   }
 
   const size_t fs = xin.fs;
@@ -418,7 +422,11 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
 template <int IN, int MODE, bool WITH_P, int EP, bool PUSH, int MINB>
 __global__ void __launch_bounds__(kBlockThreads, MINB) k_stokes_x(const __grid_constant__ StokesArgs a) {
   const int rows = a.g.rows;
-  const int r0 = blockIdx.y * a.g.rs;
+  // strip order: first strip, LAST strip, then the interior -- both edge strips (the ones that wait for the ring
+  // neighbours' rows and push this rank's own) run in the first wave and their transfers overlap the interior
+  const int S = (int)gridDim.y, sy = (int)blockIdx.y;
+  const int strip = (S > 2) ? (sy == 0 ? 0 : (sy == 1 ? S - 1 : sy - 1)) : sy;
+  const int r0 = strip * a.g.rs;
   if (r0 >= rows) return;
   const int r1 = min(r0 + a.g.rs, rows);
   // interior strips touch rows r0-2 .. r1+1 (and the coarse rows under them) only: all inside the slab

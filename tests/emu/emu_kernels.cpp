@@ -253,7 +253,8 @@ void emu_slab_apply_A(int P, int rounds, int n, const double* prm, const double*
     for (int g = 0; g < P; ++g) {
       const int prev = (g + P - 1) % P, next = (g + 1) % P;
       emu::launch(dim3((5 * n + 255) / 256), dim3(256), [&] {
-        k_halo_push(xs[g].data(), 5, fs, rows, n, comm[prev].data(), comm[next].data(), area, &dseq[g], &counter[g]);
+        k_halo_push(xs[g].data(), 5, fs, rows, n, comm[prev].data(), comm[next].data(), comm[g].data(), area, &dseq[g],
+                    &counter[g]);
       });
     }
     for (int g = 0; g < P; ++g) {
@@ -315,7 +316,8 @@ void emu_slab_fused_push_chain(int P, int n, const double* prm, const double* th
   for (int g = 0; g < P; ++g) {
     const int prev = (g + P - 1) % P, next = (g + 1) % P;
     emu::launch(dim3((4 * n + 255) / 256), dim3(256), [&] {
-      k_halo_push(xa[g].data(), 4, fs, rows, n, comm[prev].data(), comm[next].data(), area, &dseq[g], &counter[g][0]);
+      k_halo_push(xa[g].data(), 4, fs, rows, n, comm[prev].data(), comm[next].data(), comm[g].data(), area, &dseq[g],
+                  &counter[g][0]);
     });
   }
   // two sweeps with fused pushes (ping-pong xa -> xb -> xa), then the residual of xa into xb
@@ -329,7 +331,7 @@ void emu_slab_fused_push_chain(int P, int n, const double* prm, const double* th
       StokesArgs a{};
       a.xin = view(g, src);
       a.th = thp[g].data(); a.b = bs[g].data(); a.y = dst; a.g = geo; a.ph = ph; a.omega = omega;
-      a.po = PushOut{comm[prev].data(), comm[next].data(), area, &dseq[g], &counter[g][4]};
+      a.po = PushOut{comm[prev].data(), comm[next].data(), comm[g].data(), area, &dseq[g], &counter[g][4]};
       emu::launch(grid, dim3(kBlockThreads), [&] {
         if (step < 2) k_stokes_x<0, 2, false, 0, true, 0>(a);
         else k_stokes_x<0, 1, false, 0, false, 0>(a);

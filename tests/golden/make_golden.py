@@ -146,16 +146,28 @@ def main():
                    Mb=M.matvec(b_vec), hist=_state["hist"], true_res=np.array(true_res), x=_state["x"],
                    err_norms=np.array(norms))
         # conditioning of the history itself: what another correct fp64 implementation of the same algorithm may
-        # legitimately return.  16 re-runs in which b AND the result of every A.x and M.v carry an independent
-        # ~1-ulp relative perturbation (a different summation order / fma contraction in any kernel does that);
-        # for FGMRES additionally the independent C restatement of the oracle (its own rounding everywhere).
-        # The envelope is the largest relative change per iteration.
+        # legitimately return.  The same Krylov driver is re-run 17 times: with the oracle's own operators (8 runs) and
+        # with the operators of the INDEPENDENT C restatement of the oracle (oracle/mpbp_oracle_c.c: its own rounding
+        # in every stencil pass; 1 plain + 8 runs), each perturbed run with an independent ~1-ulp relative perturbation
+        # of b and of the result of every A.x and M.v (a different summation order / fma contraction does that).
+        # For FGMRES the C oracle's own Krylov driver adds three more runs.  The envelope is the largest relative
+        # change of the history per iteration over all of them.
         import scipy.sparse.linalg as spla
+        import c_oracle
+        ckw = dict(kind=cfgF.kind, F_cycles=cfgF.cycles, P_cycles=cfgF.cycles, F_sweeps=cfgF.sweeps, P_sweeps=cfgF.sweeps,
+                   omega=cfgF.omega, cheb=cfgF.cheb)
+        co = c_oracle.COracle(n, xi, eta_n, eta_s, c, d, **ckw)
+        m5 = len(b_vec)
 
-        def noisy(op, prng):
-            f = (lambda z: op @ z) if not hasattr(op, "matvec") else op.matvec
-            return spla.LinearOperator((len(b_vec), len(b_vec)), dtype=np.float64,
-                                       matvec=lambda z: f(z) * (1.0 + 1.2e-16 * prng.standard_normal(len(b_vec))))
+        def wrap(f, prng):
+            if prng is None:
+                return spla.LinearOperator((m5, m5), dtype=np.float64, matvec=f)
+            return spla.LinearOperator((m5, m5), dtype=np.float64,
+                                       matvec=lambda z: f(z) * (1.0 + 1.2e-16 * prng.standard_normal(m5)))
+        A_np = lambda z: A @ z
+        M_np = M.matvec
+        A_c = lambda z: co.apply_A(np.ascontiguousarray(z))
+        M_c = lambda z: co.precond(np.ascontiguousarray(z))
 
         def envelope(run, h0, extra=()):
             env = np.zeros(len(h0))
@@ -166,9 +178,11 @@ def main():
                 env[:k] = np.maximum(env[:k], np.abs(h[:k] - h0[:k]) / h0[:k])
                 if len(h) != len(h0):
                     env[k:] = np.inf
-            for _ in range(16):  # >= 16 perturbed runs per envelope
+            fold(run(b_vec, wrap(A_c, None), wrap(M_c, None)))
+            for i in range(16):  # 16 perturbed runs per envelope, alternating between the two implementations
                 bp_ = b_vec * (1.0 + 1.2e-16 * prng.standard_normal(b_vec.shape))
-                fold(run(bp_, noisy(A, prng), noisy(M, prng)))
+                fa, fm = (A_np, M_np) if i % 2 == 0 else (A_c, M_c)
+                fold(run(bp_, wrap(fa, prng), wrap(fm, prng)))
             for h in extra:
                 fold(h)
             return env
@@ -177,9 +191,6 @@ def main():
             O.fgmres(Aop, bb, M=Mop, tol=1e-8, maxiter=150)
             return O.fgmres.last_history.copy()
 
-        import c_oracle
-        ckw = dict(kind=cfgF.kind, F_cycles=cfgF.cycles, P_cycles=cfgF.cycles, F_sweeps=cfgF.sweeps, P_sweeps=cfgF.sweeps,
-                   omega=cfgF.omega, cheb=cfgF.cheb)
         c_hists = []
         for threads in (1, 3, 8):
             c_oracle.set_threads(threads)
