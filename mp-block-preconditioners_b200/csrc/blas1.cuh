@@ -61,14 +61,68 @@ __device__ __forceinline__ bool last_block(unsigned int* counter) {
   return is_last;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// All-reduce (sum) of a few scalars over the ranks through peer memory, fused into the reduction kernels: the last
+// block of the local reduction stores its partial sums into EVERY rank's comm buffer (NVLink peer stores), releases
+// a per-(slot, source rank) flag there, waits until all ranks' contributions have arrived in its own buffer and adds
+// them in rank order -- the result is bitwise identical on all ranks and no NCCL kernel is launched (an 8-byte
+// ncclAllReduce costs 10-20 us, j+2 of them per Arnoldi step).  Operation number *rseq (the same on all ranks)
+// alternates between two slots; a rank can only reach operation k+2 after it has seen every rank's flag of k+1,
+// which each rank released after it had finished reading slot k&1.
+constexpr int kRedMaxVals = 16;
+constexpr int kRedMaxRanks = 8;
+constexpr size_t kRedBytes = 4096;
+struct RedCtx {
+  char* peers[kRedMaxRanks];  // every rank's reduction area (mapped peer memory); peers[rank] is this rank's own
+  int rank, nranks;           // nranks <= 1: no exchange
+  unsigned long long* rseq;   // device-resident operation counter
+};
+__device__ __forceinline__ unsigned long long* red_flag(char* area, int slot, int src) {
+  return reinterpret_cast<unsigned long long*>(area) + slot * kRedMaxRanks + src;
+}
+__device__ __forceinline__ double* red_vals(char* area, int slot, int src) {
+  return reinterpret_cast<double*>(area + 256) + (size_t)(slot * kRedMaxRanks + src) * kRedMaxVals;
+}
+// called by every thread of ONE block; vals: `count` block-visible doubles (shared memory), overwritten by the sums
+__device__ __forceinline__ void p2p_allreduce_sum(const RedCtx& rc, double* vals, int count) {
+  if (rc.nranks <= 1) return;
+  const unsigned long long seq = *rc.rseq + 1ull;
+  const int slot = (int)(seq & 1ull);
+  const int t = threadIdx.x;
+  if (t < rc.nranks * count) {
+    const int r = t / count, i = t - r * count;
+    red_vals(rc.peers[r], slot, rc.rank)[i] = vals[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < rc.nranks) {
+    unsigned long long* f = red_flag(rc.peers[t], slot, rc.rank);
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(seq) : "memory");
+    const unsigned long long* mine = red_flag(rc.peers[rc.rank], slot, t);
+    unsigned long long got;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(mine) : "memory");
+    } while (got < seq);
+  }
+  __syncthreads();
+  if (t < count) {
+    double s = 0.0;
+    for (int r = 0; r < rc.nranks; ++r) s += __ldcg(red_vals(rc.peers[rc.rank], slot, r) + t);
+    vals[t] = s;
+  }
+  __syncthreads();
+  if (t == 0) *rc.rseq = seq;
+}
+
 // out[k] = sum_i V_k[i] * w[i], k < NV (V_k = V + k*ld).  partial: gridDim.x * NV doubles.
 // post: 0 none, 1 sqrt (nrm2 on one rank)
 template <int NV>
 __global__ void __launch_bounds__(kRedThreads) k_multi_dot(const double* __restrict__ V, size_t ld,
                                                            const double* __restrict__ w, size_t len,
                                                            double* __restrict__ partial, unsigned int* counter,
-                                                           double* __restrict__ out, int post) {
+                                                           double* __restrict__ out, int post, RedCtx rc) {
   __shared__ double smem[kRedThreads / 32];
+  __shared__ double red_sh[kRedMaxVals];
   double acc[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) acc[k] = 0.0;
@@ -106,8 +160,11 @@ __global__ void __launch_bounds__(kRedThreads) k_multi_dot(const double* __restr
       double s = 0.0;
       for (int bI = threadIdx.x; bI < (int)gridDim.x; bI += blockDim.x) s += partial[(size_t)bI * NV + k];
       s = block_sum(s, smem);
-      if (threadIdx.x == 0) out[k] = (post == 1) ? sqrt(s) : s;
+      if (threadIdx.x == 0) red_sh[k] = s;
     }
+    __syncthreads();
+    p2p_allreduce_sum(rc, red_sh, NV);
+    if (threadIdx.x < NV) out[threadIdx.x] = (post == 1) ? sqrt(red_sh[threadIdx.x]) : red_sh[threadIdx.x];
     if (threadIdx.x == 0) *counter = 0u;
   }
 }
@@ -122,8 +179,9 @@ __global__ void __launch_bounds__(kRedThreads) k_mgs_fused(const double* __restr
                                                            const double* __restrict__ v_next, double* __restrict__ w,
                                                            size_t len, double* __restrict__ partial,
                                                            unsigned int* counter, double* __restrict__ out_dot,
-                                                           double* __restrict__ out_nrm, int post_sqrt) {
+                                                           double* __restrict__ out_nrm, int post_sqrt, RedCtx rc) {
   __shared__ double smem[kRedThreads / 32];
+  __shared__ double red_sh[kRedMaxVals];
   double acc = 0.0, accn = 0.0;
   double al = 0.0;
   if (HAS_PREV) al = -alpha_dev[0];
@@ -175,23 +233,35 @@ __global__ void __launch_bounds__(kRedThreads) k_mgs_fused(const double* __restr
       double s = 0.0;
       for (int bI = threadIdx.x; bI < (int)gridDim.x; bI += blockDim.x) s += partial[2 * bI];
       s = block_sum(s, smem);
-      if (threadIdx.x == 0) out_dot[0] = s;
+      if (threadIdx.x == 0) red_sh[0] = s;
     }
     if (NRM) {
       double s = 0.0;
       for (int bI = threadIdx.x; bI < (int)gridDim.x; bI += blockDim.x) s += partial[2 * bI + 1];
       s = block_sum(s, smem);
-      if (threadIdx.x == 0) out_nrm[0] = post_sqrt ? sqrt(s) : s;
+      if (threadIdx.x == 0) red_sh[1] = s;
     }
-    if (threadIdx.x == 0) *counter = 0u;
+    __syncthreads();
+    if (rc.nranks > 1) {
+      if (!HAS_NEXT && threadIdx.x == 0) red_sh[0] = 0.0;
+      if (!NRM && threadIdx.x == 0) red_sh[1] = 0.0;
+      __syncthreads();
+      p2p_allreduce_sum(rc, red_sh, 2);
+    }
+    if (threadIdx.x == 0) {
+      if (HAS_NEXT) out_dot[0] = red_sh[0];
+      if (NRM) out_nrm[0] = post_sqrt ? sqrt(red_sh[1]) : red_sh[1];
+      *counter = 0u;
+    }
   }
 }
 
 // out[0] = sum x  (used for the mean removal, solve.py:260-264)
 __global__ void __launch_bounds__(kRedThreads) k_sum(const double* __restrict__ x, size_t len,
                                                      double* __restrict__ partial, unsigned int* counter,
-                                                     double* __restrict__ out) {
+                                                     double* __restrict__ out, RedCtx rc) {
   __shared__ double smem[kRedThreads / 32];
+  __shared__ double red_sh[kRedMaxVals];
   double acc = 0.0;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) acc += x[i];
@@ -201,8 +271,11 @@ __global__ void __launch_bounds__(kRedThreads) k_sum(const double* __restrict__ 
     double t = 0.0;
     for (int bI = threadIdx.x; bI < (int)gridDim.x; bI += blockDim.x) t += partial[bI];
     t = block_sum(t, smem);
+    if (threadIdx.x == 0) red_sh[0] = t;
+    __syncthreads();
+    p2p_allreduce_sum(rc, red_sh, 1);
     if (threadIdx.x == 0) {
-      out[0] = t;
+      out[0] = red_sh[0];
       *counter = 0u;
     }
   }

@@ -67,7 +67,8 @@ struct Level {
   double *bF = nullptr, *xF = nullptr, *tF = nullptr, *rF = nullptr;  // 4*rows*n each
   double *bP = nullptr, *xP = nullptr, *tP = nullptr, *rP = nullptr;  // rows*n each
   double *gF = nullptr, *gP = nullptr;  // restricted slab before the all-gather (first replicated level only)
-  double* wdF = nullptr;                // omega / diag(F), 4N (whole-grid levels; fused pre-smoothing)
+  double* wdF = nullptr;                // omega / diag(F), 4N (fused pre-smoothing)
+  double* wdh = nullptr;                // dist: the ring neighbours' boundary rows of wdF, [2][4][n] (static)
   size_t fs() const { return (size_t)rows * n; }
 };
 
@@ -123,7 +124,7 @@ struct mpbp_plan {
   int fuse = 7;
   // experimental (MPBP_PUSH_FUSED=1): smoothing / residual kernels on distributed levels push their own boundary
   // rows to the neighbours; the next stencil kernel on that vector then skips its k_halo_push
-  bool push_fused = false;
+  bool push_fused = true;
   const double* pending_push = nullptr;  // vector whose halo rows the last kernel already pushed
   int coarse_n = 0;  // experimental (MPBP_COARSE=<n>): whole-grid levels with n <= coarse_n run as ONE persistent kernel
   bool fused_mgs = true;
@@ -137,6 +138,8 @@ struct mpbp_plan {
   char *comm_prev = nullptr, *comm_next = nullptr;  // neighbours' comm buffers mapped into this process
   size_t comm_area = 0;                     // doubles per (slot, direction) halo area
   unsigned long long* dseq = nullptr;       // device-resident exchange counter (identical on all ranks)
+  std::vector<char*> comm_all;              // every rank's comm buffer mapped here (index = rank; own = comm_local)
+  RedCtx red{};                             // peer-memory all-reduce of the reduction kernels (nranks <= 1: off)
 };
 
 
@@ -201,7 +204,10 @@ static void carve(mpbp_plan* p, Bump& B) {
       v.bP = B.take<double>(fs);
       v.xP = B.take<double>(fs);
     }
-    if (!v.dist && l < L - 1 && !p->cfg.operators_only) v.wdF = B.take<double>(4 * fs);
+    if (l < L - 1 && !p->cfg.operators_only) {
+      v.wdF = B.take<double>(4 * fs);
+      if (v.dist) v.wdh = B.take<double>((size_t)2 * 4 * v.n);
+    }
     if (l == p->first_repl) {
       const Level& f = p->lev[l - 1];
       v.gF = B.take<double>(4 * (f.fs() / 4));
@@ -301,6 +307,22 @@ static int halo_exchange(mpbp_plan* p, Level& v, const double* x, int nf, size_t
   return 0;
 }
 
+// one-off (plan creation) fetch of the ring neighbours' boundary rows of a static per-level field into `dst`
+// ([2][nf][n]: top rows, then bottom rows) with NCCL send/recv
+static int fetch_static_halo(mpbp_plan* p, Level& v, const double* x, int nf, double* dst) {
+  const int P = p->nranks, prev = (p->rank + P - 1) % P, next = (p->rank + 1) % P;
+  const size_t n = v.n, fs = v.fs();
+  NC(ncclGroupStart());
+  for (int k = 0; k < nf; ++k) {
+    NC(ncclSend(x + k * fs + (size_t)(v.rows - 1) * n, n, ncclDouble, next, p->comm, p->st));
+    NC(ncclSend(x + k * fs, n, ncclDouble, prev, p->comm, p->st));
+    NC(ncclRecv(dst + k * n, n, ncclDouble, prev, p->comm, p->st));
+    NC(ncclRecv(dst + (size_t)nf * n + k * n, n, ncclDouble, next, p->comm, p->st));
+  }
+  NC(ncclGroupEnd());
+  return 0;
+}
+
 // view of a level vector for stencil kernels (performs the halo exchange when distributed)
 static int make_view(mpbp_plan* p, Level& v, const double* x, int nf, VecIn& out) {
   const size_t fs = v.fs();
@@ -335,6 +357,9 @@ static int allreduce_scal(mpbp_plan* p, double* dev, int count) {
 }
 
 // ---- operator launches -----------------------------------------------------------------------
+static inline PushOut push_out(mpbp_plan* p) {
+  return PushOut{p->comm_prev, p->comm_next, p->comm_local, p->comm_area, p->dseq, p->counter + 40};
+}
 // one launch of the unified marching kernel (csrc/stokes.cuh); `a` carries the variant's extra arguments
 struct SxKind {
   int in = 0, mode = 0, ep = 0;
@@ -350,10 +375,10 @@ static int launch_sx(mpbp_plan* p, int l, SxKind k, StokesArgs& a) {
   a.g = v.geo;
   a.ph = v.ph;
   const int wc = (k.ep == 2) ? WarpTile<2>::cols : WarpTile<0>::cols;
-  if ((k.in == 2 || k.ep == 2) && ((v.rows & 1) || (v.geo.rs & 1) || v.dist))
+  if ((k.in == 2 || k.ep == 2) && ((v.rows & 1) || (v.geo.rs & 1) || (v.dist && k.ep == 2)))
     return set_err(MPBP_E_STATE, "internal: row-pair kernel on an odd / distributed level (rows %d, rs %d)", v.rows, v.geo.rs);
   const dim3 grid((unsigned)((v.n + wc * kBlockWarps - 1) / (wc * kBlockWarps)), (unsigned)((v.rows + v.geo.rs - 1) / v.geo.rs));
-  if (k.push) a.po = PushOut{p->comm_prev, p->comm_next, p->comm_local, p->comm_area, p->dseq, p->counter + 40};
+  if (k.push) a.po = push_out(p);
   const int key = k.in * 10000 + k.mode * 1000 + (k.with_p ? 100 : 0) + k.ep * 10 + (k.push ? 1 : 0);
   switch (key) {
     case 100: sx_launch<0, 0, true, 0, false, 5>(p, grid, a); break;    // y = A x
@@ -368,7 +393,9 @@ static int launch_sx(mpbp_plan* p, int l, SxKind k, StokesArgs& a) {
     case 12001: sx_launch<1, 2, false, 0, true, 5>(p, grid, a); break;
     case 1020: sx_launch<0, 1, false, 2, false, 5>(p, grid, a); break;   // residual + restriction
     case 22000: sx_launch<2, 2, false, 0, false, 4>(p, grid, a); break;  // prolongation + first post-sweep
+    case 22001: sx_launch<2, 2, false, 0, true, 4>(p, grid, a); break;
     case 22010: sx_launch<2, 2, false, 1, false, 4>(p, grid, a); break;  // ... which is also the last one
+    case 22011: sx_launch<2, 2, false, 1, true, 4>(p, grid, a); break;
     default: return set_err(MPBP_E_STATE, "internal: no stokes kernel variant %d", key);
   }
   LAUNCH_CHECK(p);
@@ -378,10 +405,11 @@ static int launch_sx(mpbp_plan* p, int l, SxKind k, StokesArgs& a) {
 // y = Op x (mode 0), b - F x (mode 1), x + omega (b - F x)/diag (mode 2); optional Chebyshev epilogue on mode 2.
 // On distributed levels the smoothing / residual kernels push their own boundary rows to the ring neighbours.
 static int op_stokes(mpbp_plan* p, int l, int mode, bool with_p, const double* x, const double* b, double* y,
-                     double omega, const ChebEp* ce = nullptr) {
+                     double omega, const ChebEp* ce = nullptr, bool stash = false) {
   Level& v = p->lev[l];
   StokesArgs a{};
   RET(make_view(p, v, x, with_p ? 5 : 4, a.xin));
+  if (stash && v.dist && p->p2p) a.stash = v.halo;
   a.b = b;
   a.y = y;
   a.omega = omega;
@@ -408,16 +436,25 @@ static int op_presmooth_pair(mpbp_plan* p, int l, const double* b, double* y) {
   Level& v = p->lev[l];
   StokesArgs a{};
   RET(make_view(p, v, b, 4, a.xin));
-  a.wd = a.xin;
   a.wd.x = v.wdF;
-  if (v.dist) return set_err(MPBP_E_STATE, "internal: fused pre-smoothing on a distributed level");
-  a.wd.top = v.wdF + (size_t)(v.rows - 1) * v.n;
-  a.wd.bot = v.wdF;
+  a.wd.fs = v.fs();
+  if (v.dist) {  // the neighbours' rows of omega/diag(F) were fetched once at plan creation
+    a.wd.top = v.wdh;
+    a.wd.bot = v.wdh + (size_t)4 * v.n;
+    a.wd.hs = v.n;
+  } else {
+    a.wd.top = v.wdF + (size_t)(v.rows - 1) * v.n;
+    a.wd.bot = v.wdF;
+    a.wd.hs = v.fs();
+  }
   a.y = y;
   SxKind k;
   k.in = 1;
   k.mode = 2;
-  return launch_sx(p, l, k, a);
+  k.push = v.dist && p->p2p && p->push_fused;
+  RET(launch_sx(p, l, k, a));
+  if (k.push) p->pending_push = y;
+  return 0;
 }
 // coarse rhs b_{l+1} = R (b - F x): residual and full-weighting restriction in one pass (whole-grid levels)
 static int op_residual_restrict(mpbp_plan* p, int l, const double* x, const double* b) {
@@ -440,13 +477,32 @@ static int op_prolong_sweep(mpbp_plan* p, int l, const double* x, const double* 
   Level& v = p->lev[l];
   Level& c = p->lev[l + 1];
   StokesArgs a{};
-  RET(make_view(p, v, x, 4, a.xin));
-  a.cin.x = c.xF;
-  a.cin.fs = a.cin.hs = c.fs();
-  a.cin.top = c.xF + (size_t)(c.rows - 1) * c.n;
-  a.cin.bot = c.xF;
+  if (v.dist) {
+    // x's halo rows were stashed by the residual kernel of this cycle (the comm slots have been recycled since)
+    a.xin.x = x;
+    a.xin.fs = v.fs();
+    a.xin.hs = v.n;
+    a.xin.top = v.halo;
+    a.xin.bot = v.halo + (size_t)5 * v.n;
+    if (l + 1 == p->first_repl) {
+      // coarse level is replicated: address this rank's rows inside the full coarse grid
+      const int R0 = v.row0 / 2, rows_c = v.rows / 2, nc = c.n;
+      a.cin.x = c.xF + (size_t)R0 * nc;
+      a.cin.fs = a.cin.hs = c.fs();
+      a.cin.top = c.xF + (size_t)((R0 + nc - 1) % nc) * nc;
+      a.cin.bot = c.xF + (size_t)((R0 + rows_c) % nc) * nc;
+    } else {
+      RET(make_view(p, c, c.xF, 4, a.cin));
+    }
+  } else {
+    RET(make_view(p, v, x, 4, a.xin));
+    a.cin.x = c.xF;
+    a.cin.fs = a.cin.hs = c.fs();
+    a.cin.top = c.xF + (size_t)(c.rows - 1) * c.n;
+    a.cin.bot = c.xF;
+  }
   a.nc = c.n;
-  a.rows_c = c.rows;
+  a.rows_c = v.rows / 2;
   a.b = b;
   a.y = y;
   a.omega = omega;
@@ -457,7 +513,10 @@ static int op_prolong_sweep(mpbp_plan* p, int l, const double* x, const double* 
     a.ce = *ce;
     k.ep = 1;
   }
-  return launch_sx(p, l, k, a);
+  k.push = v.dist && p->p2p && p->push_fused;
+  RET(launch_sx(p, l, k, a));
+  if (k.push) p->pending_push = ce ? ce->xk : y;
+  return 0;
 }
 static int op_poisson(mpbp_plan* p, int l, int mode, const double* x, const double* b, double* y, double omega,
                       const ChebEp* ce = nullptr) {
@@ -465,19 +524,33 @@ static int op_poisson(mpbp_plan* p, int l, int mode, const double* x, const doub
   VecIn in{};
   if (mode != 3) RET(make_view(p, v, x, 1, in));
   const dim3 grid = stencil_grid(v, v.geoL), block(kBlockThreads);
+  // distributed levels: the sweeps push their own boundary rows (the residual's consumer, the cell-average
+  // restriction, needs no halo)
+  const bool push = v.dist && p->p2p && p->push_fused && mode >= 2;
+  const PushOut po = push ? push_out(p) : PushOut{};
   if (ce) {
     if (mode != 2) return set_err(MPBP_E_STATE, "internal: Chebyshev epilogue on a non-sweep");
-    k_poisson<2, true><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geoL, v.ph, omega, *ce);
+    if (push) k_poisson<2, true, true><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geoL, v.ph, omega, *ce, po);
+    else k_poisson<2, true, false><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geoL, v.ph, omega, *ce, po);
     LAUNCH_CHECK(p);
+    if (push) p->pending_push = ce->xk;
     return 0;
   }
+  const ChebEp none{};
   switch (mode) {
-    case 0: k_poisson<0><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geoL, v.ph, omega); break;
-    case 1: k_poisson<1><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geoL, v.ph, omega); break;
-    case 2: k_poisson<2><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geoL, v.ph, omega); break;
-    default: k_poisson<3><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geoL, v.ph, omega); break;
+    case 0: k_poisson<0><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geoL, v.ph, omega, none, po); break;
+    case 1: k_poisson<1><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geoL, v.ph, omega, none, po); break;
+    case 2:
+      if (push) k_poisson<2, false, true><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geoL, v.ph, omega, none, po);
+      else k_poisson<2><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geoL, v.ph, omega, none, po);
+      break;
+    default:
+      if (push) k_poisson<3, false, true><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geoL, v.ph, omega, none, po);
+      else k_poisson<3><<<grid, block, 0, p->st>>>(in, v.th, b, y, v.geoL, v.ph, omega, none, po);
+      break;
   }
   LAUNCH_CHECK(p);
+  if (push) p->pending_push = y;
   return 0;
 }
 // r = scale * D w + add
@@ -495,8 +568,11 @@ static int op_grad(mpbp_plan* p, int l, const double* pr, double* y) {
   Level& v = p->lev[l];
   VecIn in{};
   RET(make_view(p, v, pr, 1, in));
-  k_grad<<<stencil_grid(v, v.geoL), kBlockThreads, 0, p->st>>>(in, v.th, y, v.fs(), v.geoL, v.ph);
+  const bool push = v.dist && p->p2p && p->push_fused;
+  if (push) k_grad<true><<<stencil_grid(v, v.geoL), kBlockThreads, 0, p->st>>>(in, v.th, y, v.fs(), v.geoL, v.ph, push_out(p));
+  else k_grad<false><<<stencil_grid(v, v.geoL), kBlockThreads, 0, p->st>>>(in, v.th, y, v.fs(), v.geoL, v.ph, PushOut{});
   LAUNCH_CHECK(p);
+  if (push) p->pending_push = y;
   return 0;
 }
 static int op_dense(mpbp_plan* p, const double* Mt, const double* x, double* y, int m) {
@@ -517,8 +593,11 @@ static int op_restrict(mpbp_plan* p, int l, bool isF, const double* r) {
     VecIn in{};
     RET(make_view(p, f, r, 4, in));
     double* dst = gather ? c.gF : c.bF;
-    k_restrict_F<<<grid, block, 0, p->st>>>(in, dst, f.n, f.rows);
+    const bool push = c.dist && p->p2p && p->push_fused;  // the coarse rhs is the input of the next level's pre-smoother
+    if (push) k_restrict_F<true><<<grid, block, 0, p->st>>>(in, dst, f.n, f.rows, push_out(p));
+    else k_restrict_F<false><<<grid, block, 0, p->st>>>(in, dst, f.n, f.rows, PushOut{});
     LAUNCH_CHECK(p);
+    if (push) p->pending_push = dst;
     if (gather) {
       const size_t cnt = (size_t)rows_c * nc;
       NC(ncclGroupStart());
@@ -555,7 +634,12 @@ static int op_prolong_add(mpbp_plan* p, int l, bool isF, double* x) {
   } else {
     const double* xc = c.xP;
     if (l + 1 == p->first_repl) xc += (size_t)(f.row0 / 2) * c.n;
-    k_prolong_add_P<<<grid, block, 0, p->st>>>(xc, x, f.n, f.rows);
+    const bool push = f.dist && p->p2p && p->push_fused;
+    if (push) k_prolong_add_P<true><<<grid, block, 0, p->st>>>(xc, x, f.n, f.rows, push_out(p));
+    else k_prolong_add_P<false><<<grid, block, 0, p->st>>>(xc, x, f.n, f.rows, PushOut{});
+    LAUNCH_CHECK(p);
+    if (push) p->pending_push = x;
+    return 0;
   }
   LAUNCH_CHECK(p);
   return 0;
@@ -576,24 +660,25 @@ static int v_copy(mpbp_plan* p, const double* x, double* y, size_t len) {
 static int v_multi_dot(mpbp_plan* p, const double* V, size_t ld, int nvec, const double* w, size_t len,
                        double* out_dev, bool post_sqrt) {
   const int blocks = (int)std::min<size_t>((len + kRedThreads - 1) / kRedThreads, (size_t)p->red_blocks);
-  const int post = (post_sqrt && p->nranks == 1) ? 1 : 0;
+  const bool fused_ar = p->red.nranks > 1;  // the all-reduce happens inside the kernel (peer memory)
+  const int post = (post_sqrt && (p->nranks == 1 || fused_ar)) ? 1 : 0;
   for (int k0 = 0; k0 < nvec; k0 += kMaxMulti) {
     const int nv = std::min(kMaxMulti, nvec - k0);
     const double* Vk = V + (size_t)k0 * ld;
     double* o = out_dev + k0;
     switch (nv) {
-      case 1: k_multi_dot<1><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post); break;
-      case 2: k_multi_dot<2><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post); break;
-      case 3: k_multi_dot<3><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post); break;
-      case 4: k_multi_dot<4><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post); break;
-      case 5: k_multi_dot<5><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post); break;
-      case 6: k_multi_dot<6><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post); break;
-      case 7: k_multi_dot<7><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post); break;
-      default: k_multi_dot<8><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post); break;
+      case 1: k_multi_dot<1><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post, p->red); break;
+      case 2: k_multi_dot<2><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post, p->red); break;
+      case 3: k_multi_dot<3><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post, p->red); break;
+      case 4: k_multi_dot<4><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post, p->red); break;
+      case 5: k_multi_dot<5><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post, p->red); break;
+      case 6: k_multi_dot<6><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post, p->red); break;
+      case 7: k_multi_dot<7><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post, p->red); break;
+      default: k_multi_dot<8><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, len, p->partial, p->counter, o, post, p->red); break;
     }
     LAUNCH_CHECK(p);
   }
-  if (p->nranks > 1) {
+  if (p->nranks > 1 && !fused_ar) {
     RET(allreduce_scal(p, out_dev, nvec));
     if (post_sqrt) {
       k_sqrt_inplace<<<1, 256, 0, p->st>>>(out_dev, nvec);
@@ -644,9 +729,10 @@ static int v_mgs(mpbp_plan* p, const double* V, size_t ld, int j, double* w, siz
     return v_nrm2(p, w, len, nrm_after);
   }
   const int blocks = (int)std::min<size_t>((len + kRedThreads - 1) / kRedThreads, (size_t)p->red_blocks);
-  const int post = p->nranks == 1 ? 1 : 0;
+  const bool fused_ar = p->red.nranks > 1;
+  const int post = (p->nranks == 1 || fused_ar) ? 1 : 0;
   auto finish = [&](double* dot, double* nrm) -> int {
-    if (p->nranks > 1) {
+    if (p->nranks > 1 && !fused_ar) {
       if (dot) RET(allreduce_scal(p, dot, 1));
       if (nrm) {
         RET(allreduce_scal(p, nrm, 1));
@@ -659,21 +745,21 @@ static int v_mgs(mpbp_plan* p, const double* V, size_t ld, int j, double* w, siz
   // first: h_0 = <V_0, w> (+ ||w||)
   if (nrm_before)
     k_mgs_fused<false, true, true><<<blocks, kRedThreads, 0, p->st>>>(nullptr, nullptr, V, w, len, p->partial, p->counter,
-                                                                      hd, nrm_before, post);
+                                                                      hd, nrm_before, post, p->red);
   else
     k_mgs_fused<false, true, false><<<blocks, kRedThreads, 0, p->st>>>(nullptr, nullptr, V, w, len, p->partial,
-                                                                       p->counter, hd, nullptr, post);
+                                                                       p->counter, hd, nullptr, post, p->red);
   LAUNCH_CHECK(p);
   RET(finish(hd, nrm_before));
   for (int k = 1; k <= j; ++k) {
     k_mgs_fused<true, true, false><<<blocks, kRedThreads, 0, p->st>>>(hd + k - 1, V + (size_t)(k - 1) * ld,
                                                                       V + (size_t)k * ld, w, len, p->partial, p->counter,
-                                                                      hd + k, nullptr, post);
+                                                                      hd + k, nullptr, post, p->red);
     LAUNCH_CHECK(p);
     RET(finish(hd + k, nullptr));
   }
   k_mgs_fused<true, false, true><<<blocks, kRedThreads, 0, p->st>>>(hd + j, V + (size_t)j * ld, nullptr, w, len, p->partial,
-                                                                    p->counter, nullptr, nrm_after, post);
+                                                                    p->counter, nullptr, nrm_after, post, p->red);
   LAUNCH_CHECK(p);
   return finish(nullptr, nrm_after);
 }
@@ -756,9 +842,10 @@ static int vcycle(mpbp_plan* p, int l, bool isF, const double* b, double* x, con
   double* t = isF ? v.tF : v.tP;
   double* r = isF ? v.rF : v.rP;
   const bool even = !(v.rows & 1) && !(v.geo.rs & 1);
-  const bool fuse_pre = isF && (p->fuse & 1) && !v.dist && c.nu1 == 2 && v.wdF != nullptr;
-  const bool fuse_rr = isF && (p->fuse & 4) && !v.dist && even;                 // residual + restriction
-  const bool fuse_post = isF && (p->fuse & 2) && !v.dist && even && c.nu2 >= 1;  // prolongation + first post-sweep
+  const bool dist_ok = !v.dist || (p->p2p && p->push_fused);  // distributed levels: fused variants need the peer-memory halos
+  const bool fuse_pre = isF && (p->fuse & 1) && dist_ok && c.nu1 == 2 && v.wdF != nullptr;
+  const bool fuse_rr = isF && (p->fuse & 4) && !v.dist && even;                  // residual + restriction
+  const bool fuse_post = isF && (p->fuse & 2) && dist_ok && even && c.nu2 >= 1;  // prolongation + first post-sweep
   // number of kernels that write the iterate into a fresh buffer (they ping-pong between x and t); the last one
   // must land in x unless it ends in the epilogue
   const int pre_w = fuse_pre ? 1 : c.nu1;
@@ -783,7 +870,7 @@ static int vcycle(mpbp_plan* p, int l, bool isF, const double* b, double* x, con
   if (fuse_rr) {
     RET(op_residual_restrict(p, l, cur, b));
   } else {
-    if (isF) RET(op_stokes(p, l, 1, false, cur, b, r, 0.0));
+    if (isF) RET(op_stokes(p, l, 1, false, cur, b, r, 0.0, nullptr, /*stash=*/fuse_post));
     else RET(op_poisson(p, l, 1, cur, b, r, 0.0));
     RET(op_restrict(p, l, isF, r));
   }
@@ -814,9 +901,9 @@ static int project_mean(mpbp_plan* p, double* x) {
   const size_t len = v.fs();
   const int blocks = (int)std::min<size_t>((len + kRedThreads - 1) / kRedThreads, (size_t)p->red_blocks);
   double* s = p->scal + kScal - 1;
-  k_sum<<<blocks, kRedThreads, 0, p->st>>>(x, len, p->partial, p->counter, s);
+  k_sum<<<blocks, kRedThreads, 0, p->st>>>(x, len, p->partial, p->counter, s, p->red);
   LAUNCH_CHECK(p);
-  RET(allreduce_scal(p, s, 1));
+  if (p->red.nranks <= 1) RET(allreduce_scal(p, s, 1));
   k_shift_dev<<<ew_blocks(len), 256, 0, p->st>>>(s, 1.0 / ((double)v.n * (double)v.n), x, len);
   LAUNCH_CHECK(p);
   return 0;
@@ -1072,7 +1159,8 @@ static int build_coarse_inverses(mpbp_plan* p) {
 static int setup_p2p(mpbp_plan* p) {
   const int P = p->nranks, prev = (p->rank + P - 1) % P, next = (p->rank + 1) % P;
   p->comm_area = (size_t)5 * p->lev[0].n;
-  const size_t bytes = kFlagBytes + 4 * p->comm_area * sizeof(double);
+  const size_t halo_bytes = (kFlagBytes + 4 * p->comm_area * sizeof(double) + 255) & ~size_t(255);
+  const size_t bytes = halo_bytes + kRedBytes;
   CU(cudaMalloc(&p->comm_local, bytes));
   CU(cudaMemset(p->comm_local, 0, bytes));
   cudaIpcMemHandle_t mine;
@@ -1085,14 +1173,24 @@ static int setup_p2p(mpbp_plan* p) {
   std::vector<cudaIpcMemHandle_t> all(P);
   CU(cudaMemcpy(all.data(), dh, (size_t)P * sizeof(mine), cudaMemcpyDeviceToHost));
   CU(cudaFree(dh));
-  void* pp = nullptr;
-  CU(cudaIpcOpenMemHandle(&pp, all[prev], cudaIpcMemLazyEnablePeerAccess));
-  p->comm_prev = (char*)pp;
-  if (next == prev) {
-    p->comm_next = p->comm_prev;
-  } else {
-    CU(cudaIpcOpenMemHandle(&pp, all[next], cudaIpcMemLazyEnablePeerAccess));
-    p->comm_next = (char*)pp;
+  // every rank's buffer is mapped: the ring neighbours' for the halo rows, all of them for the fused all-reduce
+  p->comm_all.assign(P, nullptr);
+  for (int r = 0; r < P; ++r) {
+    if (r == p->rank) {
+      p->comm_all[r] = p->comm_local;
+      continue;
+    }
+    void* pp = nullptr;
+    CU(cudaIpcOpenMemHandle(&pp, all[r], cudaIpcMemLazyEnablePeerAccess));
+    p->comm_all[r] = (char*)pp;
+  }
+  p->comm_prev = p->comm_all[prev];
+  p->comm_next = p->comm_all[next];
+  if (P <= kRedMaxRanks && !getenv("MPBP_NCCL_ALLREDUCE")) {
+    p->red.rank = p->rank;
+    p->red.nranks = P;
+    p->red.rseq = p->dseq + 8;
+    for (int r = 0; r < P; ++r) p->red.peers[r] = p->comm_all[r] + halo_bytes;
   }
   // nobody may push before every rank has zeroed and mapped its buffers
   double* tok = nullptr;
@@ -1276,6 +1374,10 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
       p->launches++;
       rc = op_jacobi0_F(p, (int)l, v.tF, v.wdF, cfg->omega);
       if (rc) return fail(rc);
+      if (v.dist) {
+        rc = fetch_static_halo(p, v, v.wdF, 4, v.wdh);
+        if (rc) return fail(rc);
+      }
     }
   }
   if (cudaDeviceSynchronize() != cudaSuccess) return fail(set_err(999, "plan setup failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -1291,8 +1393,8 @@ extern "C" int mpbp_plan_destroy(mpbp_plan* p) {
   // waits for them
   if (p->gexec_apply) cudaGraphExecDestroy(p->gexec_apply);
   cudaDeviceSynchronize();
-  if (p->comm_prev) cudaIpcCloseMemHandle(p->comm_prev);
-  if (p->comm_next && p->comm_next != p->comm_prev) cudaIpcCloseMemHandle(p->comm_next);
+  for (size_t r = 0; r < p->comm_all.size(); ++r)
+    if (p->comm_all[r] && p->comm_all[r] != p->comm_local) cudaIpcCloseMemHandle(p->comm_all[r]);
   // (destroy is not collective: callers finish all solves on every rank before dropping their plans;
   //  ncclCommAbort never waits for the other ranks)
   if (p->comm) ncclCommAbort(p->comm);
@@ -1494,9 +1596,10 @@ static double vcycle_bytes(const mpbp_plan* p, int l, bool isF, bool with_ep) {
   // the epilogue replaces the write of z (4N or N doubles) by read d, x + write d, x (upper bound: middle cycles)
   const double ep_extra = with_ep ? (isF ? 4 : 1) * 8.0 * N * 3.0 : 0.0;
   if (isF) {
-    const bool fuse_pre = (p->fuse & 1) && !v.dist && c.nu1 == 2 && v.wdF != nullptr;
+    const bool dist_ok = !v.dist || (p->p2p && p->push_fused);
+    const bool fuse_pre = (p->fuse & 1) && dist_ok && c.nu1 == 2 && v.wdF != nullptr;
     const bool fuse_rr = (p->fuse & 4) && !v.dist && even;
-    const bool fuse_post = (p->fuse & 2) && !v.dist && even && c.nu2 >= 1;
+    const bool fuse_post = (p->fuse & 2) && dist_ok && even && c.nu2 >= 1;
     by += fuse_pre ? 104 * N : 72 * N + (c.nu1 - 1) * 104.0 * N;   // pre-smoothing (pair: reads b, omega/diag, theta)
     by += fuse_rr ? 80 * N : (104 + 40) * N;                         // residual (+ restriction: writes N instead of 4N)
     by += fuse_post ? 112 * N + (c.nu2 - 1) * 104.0 * N              // prolongation fused into the first post-sweep

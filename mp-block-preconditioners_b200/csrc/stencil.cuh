@@ -255,6 +255,60 @@ struct PushOut {
   unsigned int* counters;     // [0] first-strip blocks done, [1] last-strip blocks done, [2] all edge blocks done
 };
 
+// A producing kernel's fused push.  Blocks that own the slab's first row (`first`) write it into the previous
+// rank's bottom halo area, blocks that own the last row (`last`) into the next rank's top area, both under
+// sequence *dseq + 1; the last such block per direction releases the neighbour's flag and the last edge block of
+// the launch bumps *dseq.  push_begin: every warp of an edge block (credit wait before the first remote store);
+// push_end: every non-exited thread of an edge block, after its last remote store.
+struct PushCtx {
+  double* prev;  // neighbour's bot area: receives my row 0
+  double* next;  // neighbour's top area: receives my row rows-1
+  unsigned long long seq;
+};
+__device__ __forceinline__ PushCtx push_begin(const PushOut& po, bool first, bool last) {
+  PushCtx c;
+  c.seq = *po.dseq + 1ull;  // bumped only after every edge block of this launch has finished
+  const int slot = (int)(c.seq & 1ull);
+  c.prev = comm_halo(po.prev_comm, po.area, slot, 1);
+  c.next = comm_halo(po.next_comm, po.area, slot, 0);
+  if (first || last) {
+    if ((threadIdx.x & 31) == 0) halo_credit(po.my_comm, c.seq, first, last);
+    __syncwarp();
+  }
+  return c;
+}
+// n_first / n_last: number of blocks of this launch that own the first / last row
+__device__ __forceinline__ void push_end(const PushOut& po, const PushCtx& c, bool first, bool last, unsigned int n_first,
+                                         unsigned int n_last, bool same_blocks) {
+  if (!(first || last)) return;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int slot = (int)(c.seq & 1ull);
+    if (first && atomicAdd(&po.counters[0], 1u) == n_first - 1) {
+      po.counters[0] = 0u;
+      __threadfence_system();
+      st_release_sys(comm_flag(po.prev_comm, slot, 1), c.seq);
+    }
+    if (last && atomicAdd(&po.counters[1], 1u) == n_last - 1) {
+      po.counters[1] = 0u;
+      __threadfence_system();
+      st_release_sys(comm_flag(po.next_comm, slot, 0), c.seq);
+    }
+    const unsigned int total = same_blocks ? n_first : n_first + n_last;
+    if (atomicAdd(&po.counters[2], 1u) == total - 1) {
+      po.counters[2] = 0u;
+      *po.dseq = c.seq;
+    }
+  }
+}
+// strip order of the marching kernels: first strip, LAST strip, then the interior -- both edge strips (the ones that
+// wait for the ring neighbours' rows and push this rank's own) run in the first wave, the interior hides the transfer
+__device__ __forceinline__ int strip_of_block() {
+  const int S = (int)gridDim.y, sy = (int)blockIdx.y;
+  return (S > 2) ? (sy == 0 ? 0 : (sy == 1 ? S - 1 : sy - 1)) : sy;
+}
+
 // (the velocity-block / full-system marching kernel with its fused variants lives in stokes.cuh)
 
 __global__ void k_fill(double* __restrict__ x, double v, size_t len) {
@@ -332,17 +386,21 @@ __global__ void __launch_bounds__(kBlockThreads) k_jacobi0_F(const double* __res
 //   MODE 0: y = GtG p ; 1: y = b - GtG p ; 2: y = p + omega (b - GtG p)/diag ; 3: y = omega b/diag
 // ------------------------------------------------------------------------------------------
 //   CHEB (MODE 2): the sweep's result z goes through the Chebyshev epilogue (ChebEp) instead of being stored
-template <int MODE, bool CHEB = false>
+//   PUSH: the result's first / last rows also go to the ring neighbours (see PushOut)
+template <int MODE, bool CHEB = false, bool PUSH = false>
 __global__ void __launch_bounds__(kBlockThreads) k_poisson(VecIn pin, const double* __restrict__ th,
                                                            const double* __restrict__ b, double* __restrict__ y,
-                                                           Geo g, Phys ph, double omega, ChebEp ce = ChebEp{}) {
+                                                           Geo g, Phys ph, double omega, ChebEp ce = ChebEp{},
+                                                           PushOut po = PushOut{}) {
   const LaneGeom lg = lane_geom(g.n);
   if (!lg.alive) return;
   const int n = g.n, rows = g.rows, c = lg.cc;
-  const int r0 = blockIdx.y * g.rs;
+  const int r0 = strip_of_block() * g.rs;
   const int r1 = min(r0 + g.rs, rows);
   if (r0 >= rows) return;
   if (MODE != 3) halo_wait(pin, r0 == 0, r1 == rows);
+  PushCtx pc{};
+  if (PUSH) pc = push_begin(po, r0 == 0, r1 == rows);
   double th_m = th_row(th, r0 - 1, n)[c];
   double th_c = th_row(th, r0, n)[c];
   double p_m = 0.0, p_c = 0.0;
@@ -378,13 +436,19 @@ __global__ void __launch_bounds__(kBlockThreads) k_poisson(VecIn pin, const doub
         const double dk = ce.read_d ? ce.d[off] : 0.0;
         const double dn = ce.ca * dk + ce.cb * out;
         if (ce.write_d) ce.d[off] = dn;
-        ce.xk[off] = (ce.read_x ? ce.xk[off] : 0.0) + dn;
+        out = (ce.read_x ? ce.xk[off] : 0.0) + dn;
+        ce.xk[off] = out;
       } else {
         y[off] = out;
+      }
+      if (PUSH) {
+        if (r == 0) pc.prev[c] = out;
+        if (r == rows - 1) pc.next[c] = out;
       }
     }
     th_m = th_c; th_c = th_p; p_m = p_c; p_c = p_p; wv_c = wv_p; Hy_c = Hy_p;
   }
+  if (PUSH) push_end(po, pc, r0 == 0, r1 == rows, gridDim.x, gridDim.x, gridDim.y == 1);
 }
 
 // r = D w (+ add): un-negated divergence of both phases (preconditioner.py:221-238, :311; solve.py:259)
@@ -394,10 +458,10 @@ __global__ void __launch_bounds__(kBlockThreads) k_div(VecIn win, const double* 
   const LaneGeom lg = lane_geom(g.n);
   if (!lg.alive) return;
   const int n = g.n, rows = g.rows, c = lg.cc;
-  const int r0 = blockIdx.y * g.rs;
+  const int r0 = strip_of_block() * g.rs;
   const int r1 = min(r0 + g.rs, rows);
   if (r0 >= rows) return;
-  halo_wait(win, r0 == 0, r1 == rows);  // both flags: see halo_wait (slot reuse needs a two-sided acquire)
+  halo_wait(win, r0 == 0, r1 == rows);
   double th_m = th_row(th, r0 - 1, n)[c];
   double th_c = th_row(th, r0, n)[c];
   double vn_c = row_ptr(win, 1, r0, rows, n)[c], vs_c = row_ptr(win, 3, r0, rows, n)[c];
@@ -421,15 +485,19 @@ __global__ void __launch_bounds__(kBlockThreads) k_div(VecIn win, const double* 
 }
 
 // y = G p for both phases (preconditioner.py:203-219, :313; solve.py:273)
+template <bool PUSH = false>
 __global__ void __launch_bounds__(kBlockThreads) k_grad(VecIn pin, const double* __restrict__ th,
-                                                        double* __restrict__ y, size_t fs, Geo g, Phys ph) {
+                                                        double* __restrict__ y, size_t fs, Geo g, Phys ph,
+                                                        PushOut po = PushOut{}) {
   const LaneGeom lg = lane_geom(g.n);
   if (!lg.alive) return;
   const int n = g.n, rows = g.rows, c = lg.cc;
-  const int r0 = blockIdx.y * g.rs;
+  const int r0 = strip_of_block() * g.rs;
   const int r1 = min(r0 + g.rs, rows);
   if (r0 >= rows) return;
   halo_wait(pin, r0 == 0, r1 == rows);
+  PushCtx pc{};
+  if (PUSH) pc = push_begin(po, r0 == 0, r1 == rows);
   double th_m = th_row(th, r0 - 1, n)[c];
   double p_m = row_ptr(pin, 0, r0 - 1, rows, n)[c];
 #pragma unroll 2
@@ -442,25 +510,34 @@ __global__ void __launch_bounds__(kBlockThreads) k_grad(VecIn pin, const double*
     const double gy = ph.dp_h * (p_m - p_c);
     if (lg.store) {
       const size_t off = (size_t)r * n + c;
-      y[off] = fu * gx;
-      y[off + fs] = fv * gy;
-      y[off + 2 * fs] = (1.0 - fu) * gx;
-      y[off + 3 * fs] = (1.0 - fv) * gy;
+      const double g0 = fu * gx, g1 = fv * gy, g2 = (1.0 - fu) * gx, g3 = (1.0 - fv) * gy;
+      y[off] = g0;
+      y[off + fs] = g1;
+      y[off + 2 * fs] = g2;
+      y[off + 3 * fs] = g3;
+      if (PUSH) {
+        if (r == 0) { pc.prev[c] = g0; pc.prev[n + c] = g1; pc.prev[2 * n + c] = g2; pc.prev[3 * n + c] = g3; }
+        if (r == rows - 1) { pc.next[c] = g0; pc.next[n + c] = g1; pc.next[2 * n + c] = g2; pc.next[3 * n + c] = g3; }
+      }
     }
     th_m = th_c; p_m = p_c;
   }
+  if (PUSH) push_end(po, pc, r0 == 0, r1 == rows, gridDim.x, gridDim.x, gridDim.y == 1);
 }
 
 // ------------------------------------------------------------------------------------------
 // grid transfers (thread per output cell; coarse cell (R,C) covers fine (2R..2R+1, 2C..2C+1))
 // ------------------------------------------------------------------------------------------
 // full weighting of the four face fields: u: (1/4,1/2,1/4) over columns x (1/2,1/2) over rows; v transposed
-__global__ void k_restrict_F(VecIn fin, double* __restrict__ yc, int nf, int rows_f) {
+template <bool PUSH = false>
+__global__ void k_restrict_F(VecIn fin, double* __restrict__ yc, int nf, int rows_f, PushOut po = PushOut{}) {
   const int nc = nf >> 1, rows_c = rows_f >> 1;
   const int C = blockIdx.x * blockDim.x + threadIdx.x;
   const int R = blockIdx.y;
   halo_wait(fin, R == 0, R == (rows_f >> 1) - 1);
-  if (C >= nc || R >= rows_c) return;
+  PushCtx pc{};
+  if (PUSH) pc = push_begin(po, R == 0, R == rows_c - 1);
+  if (C < nc && R < rows_c) {
   const size_t fsc = (size_t)rows_c * nc;
   const int c0 = 2 * C, cm = (c0 == 0) ? nf - 1 : c0 - 1, cp = c0 + 1;
   const int ra = 2 * R, rb = 2 * R + 1;
@@ -469,13 +546,21 @@ __global__ void k_restrict_F(VecIn fin, double* __restrict__ yc, int nf, int row
     const double* ua = row_ptr(fin, 2 * ph, ra, rows_f, nf);
     const double* ub = row_ptr(fin, 2 * ph, rb, rows_f, nf);
     const double um = 0.5 * (ua[cm] + ub[cm]), u0 = 0.5 * (ua[c0] + ub[c0]), up = 0.5 * (ua[cp] + ub[cp]);
-    yc[(2 * ph) * fsc + (size_t)R * nc + C] = 0.25 * um + 0.5 * u0 + 0.25 * up;
+    const double cu = 0.25 * um + 0.5 * u0 + 0.25 * up;
+    yc[(2 * ph) * fsc + (size_t)R * nc + C] = cu;
     const double* vm = row_ptr(fin, 2 * ph + 1, ra - 1, rows_f, nf);
     const double* v0 = row_ptr(fin, 2 * ph + 1, ra, rows_f, nf);
     const double* vp = row_ptr(fin, 2 * ph + 1, rb, rows_f, nf);
     const double wm = 0.5 * (vm[c0] + vm[cp]), w0 = 0.5 * (v0[c0] + v0[cp]), wp = 0.5 * (vp[c0] + vp[cp]);
-    yc[(2 * ph + 1) * fsc + (size_t)R * nc + C] = 0.25 * wm + 0.5 * w0 + 0.25 * wp;
+    const double cv = 0.25 * wm + 0.5 * w0 + 0.25 * wp;
+    yc[(2 * ph + 1) * fsc + (size_t)R * nc + C] = cv;
+    if (PUSH) {
+      if (R == 0) { pc.prev[(2 * ph) * nc + C] = cu; pc.prev[(2 * ph + 1) * nc + C] = cv; }
+      if (R == rows_c - 1) { pc.next[(2 * ph) * nc + C] = cu; pc.next[(2 * ph + 1) * nc + C] = cv; }
+    }
   }
+  }
+  if (PUSH) push_end(po, pc, R == 0, R == rows_c - 1, gridDim.x, gridDim.x, gridDim.y == 1);
 }
 
 // x_f += P x_c, P = 4 R^T: u linear in x / constant in y, v linear in y / constant in x
@@ -512,12 +597,23 @@ __global__ void k_restrict_P(const double* __restrict__ f, double* __restrict__ 
 }
 
 // x_f += piecewise-constant prolongation of x_c
-__global__ void k_prolong_add_P(const double* __restrict__ xc, double* __restrict__ xf, int nf, int rows_f) {
+template <bool PUSH = false>
+__global__ void k_prolong_add_P(const double* __restrict__ xc, double* __restrict__ xf, int nf, int rows_f,
+                                PushOut po = PushOut{}) {
   const int nc = nf >> 1;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;
-  if (c >= nf || r >= rows_f) return;
-  xf[(size_t)r * nf + c] += xc[(size_t)(r >> 1) * nc + (c >> 1)];
+  PushCtx pc{};
+  if (PUSH) pc = push_begin(po, r == 0, r == rows_f - 1);
+  if (c < nf && r < rows_f) {
+    const double v = xf[(size_t)r * nf + c] + xc[(size_t)(r >> 1) * nc + (c >> 1)];
+    xf[(size_t)r * nf + c] = v;
+    if (PUSH) {
+      if (r == 0) pc.prev[c] = v;
+      if (r == rows_f - 1) pc.next[c] = v;
+    }
+  }
+  if (PUSH) push_end(po, pc, r == 0, r == rows_f - 1, gridDim.x, gridDim.x, gridDim.y == 1);
 }
 
 #ifndef MPBP_EMU

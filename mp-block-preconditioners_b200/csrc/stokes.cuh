@@ -36,6 +36,9 @@ struct StokesArgs {
   ChebEp ce;                 // EP 1
   double* bc;                // EP 2: coarse rhs, field stride rows_c*nc
   PushOut po;                // PUSH
+  double* stash;             // distributed levels: edge strips copy the halo rows they received to this static
+                             // [2][5][n] buffer, so a later kernel (prolongation + sweep) can read them again
+                             // after newer exchanges have recycled the comm slots
 };
 
 template <int EP>
@@ -67,22 +70,20 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
   if (EDGE) {
     halo_wait(xin, r0 == 0, r1 == rows);
     if (IN == 2) halo_wait(cin, r0 == 0, r1 == rows);
+    if (a.stash != nullptr && xin.dseq != nullptr && lane >= LOFF && lane < LOFF + WC && j < n) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (r0 == 0) a.stash[k * n + c] = xin.top[k * xin.hs + c];
+        if (r1 == rows) a.stash[(5 + k) * n + c] = xin.bot[k * xin.hs + c];
+      }
+    }
   }
 
   // PUSH: my first / last output rows also go to the ring neighbours' halo areas (peer memory over NVLink)
-  unsigned long long seq_out = 0ull;
-  double* push_prev = nullptr;
-  double* push_next = nullptr;
-  if (PUSH) {
-    seq_out = *a.po.dseq + 1ull;
-    const int slot = (int)(seq_out & 1ull);
-    push_prev = comm_halo(a.po.prev_comm, a.po.area, slot, 1);
-    push_next = comm_halo(a.po.next_comm, a.po.area, slot, 0);
-    if (EDGE && (r0 == 0 || r1 == rows)) {
-      if (lane == 0) halo_credit(a.po.my_comm, seq_out, r0 == 0, r1 == rows);
-      __syncwarp();
-    }
-  }
+  PushCtx pc{};
+  if (PUSH) pc = push_begin(a.po, EDGE && r0 == 0, EDGE && r1 == rows);
+  double* const push_prev = pc.prev;
+  double* const push_next = pc.next;
 
   const size_t fs = xin.fs;
   const double* __restrict__ th = a.th;
@@ -112,9 +113,11 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
   // IN 2: the coarse correction P e_c at (row rr, my column).  u-type fields (k even) are constant in y and linear
   // in x, v-type fields linear in y and constant in x (P = 4 R^T of k_restrict_F's full weighting).  The coarse rows
   // are re-read per fine row: each is shared by two fine rows and two lanes, so these are L1 hits.
-  const int fsc32 = a.rows_c * nc;
+  const int fsc32 = a.rows_c * nc;   // EP 2: field stride of the coarse rhs
+  const int fsci = (int)cin.fs;      // IN 2: field stride of the coarse correction (a replicated coarse level is addressed
+                                     // inside its full grid, so this is not rows_c*nc there)
   auto crow = [&](int k, int R) -> const double* {
-    if (!EDGE) return cin.x + (k * fsc32 + R * nc);
+    if (!EDGE) return cin.x + (k * fsci + R * nc);
     return row_ptr(cin, k, R, a.rows_c, nc);
   };
   auto pe = [&](int k, int rr, bool odd_row) -> double {
@@ -391,32 +394,7 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
     }
   }
 
-  if (PUSH) {
-    const bool first = (r0 == 0), last = (r1 == rows);
-    if (first || last) {
-      __threadfence_system();
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        const unsigned int gx = gridDim.x;
-        const int slot = (int)(seq_out & 1ull);
-        if (first && atomicAdd(&a.po.counters[0], 1u) == gx - 1) {
-          a.po.counters[0] = 0u;
-          __threadfence_system();
-          st_release_sys(comm_flag(a.po.prev_comm, slot, 1), seq_out);
-        }
-        if (last && atomicAdd(&a.po.counters[1], 1u) == gx - 1) {
-          a.po.counters[1] = 0u;
-          __threadfence_system();
-          st_release_sys(comm_flag(a.po.next_comm, slot, 0), seq_out);
-        }
-        const unsigned int total = gx * ((gridDim.y == 1) ? 1u : 2u);
-        if (atomicAdd(&a.po.counters[2], 1u) == total - 1) {
-          a.po.counters[2] = 0u;
-          *a.po.dseq = seq_out;
-        }
-      }
-    }
-  }
+  if (PUSH) push_end(a.po, pc, r0 == 0, r1 == rows, gridDim.x, gridDim.x, gridDim.y == 1);
 }
 
 template <int IN, int MODE, bool WITH_P, int EP, bool PUSH, int MINB>
@@ -424,9 +402,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) k_stokes_x(const __grid_c
   const int rows = a.g.rows;
   // strip order: first strip, LAST strip, then the interior -- both edge strips (the ones that wait for the ring
   // neighbours' rows and push this rank's own) run in the first wave and their transfers overlap the interior
-  const int S = (int)gridDim.y, sy = (int)blockIdx.y;
-  const int strip = (S > 2) ? (sy == 0 ? 0 : (sy == 1 ? S - 1 : sy - 1)) : sy;
-  const int r0 = strip * a.g.rs;
+  const int r0 = strip_of_block() * a.g.rs;
   if (r0 >= rows) return;
   const int r1 = min(r0 + a.g.rs, rows);
   // interior strips touch rows r0-2 .. r1+1 (and the coarse rows under them) only: all inside the slab

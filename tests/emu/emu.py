@@ -151,3 +151,12 @@ def slab_fused_push_chain(P, n, prm, theta, x0, b, rs=4, omega=0.8):
     th = np.ascontiguousarray(theta, dtype=np.float64)
     load().emu_slab_fused_push_chain(P, n, _p(prm), _p(th), _p(x0), _p(b), _p(out), rs, C.c_double(omega))
     return out
+
+
+def slab_fused_vcycle_chain(P, n, prm, theta, b, wd, ec, rs=4, omega=0.8):
+    c = lambda v: np.ascontiguousarray(v, dtype=np.float64)
+    b, wd, ec, th = c(b), c(wd), c(ec), c(theta)
+    out_x, out_r = np.zeros_like(b), np.zeros_like(b)
+    load().emu_slab_fused_vcycle_chain(P, n, _p(prm), _p(th), _p(b), _p(wd), _p(ec), _p(out_x), _p(out_r), rs,
+                                       C.c_double(omega))
+    return out_x, out_r

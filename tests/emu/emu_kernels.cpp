@@ -152,7 +152,7 @@ void emu_div_grad(int what, int n, const double* prm, const double* th_pad, cons
     ph.inv_h *= scale;
     emu::launch(sgrid(n, rs), dim3(kBlockThreads), [&] { k_div(in, th_pad, add, out, g, ph); });
   } else {
-    emu::launch(sgrid(n, rs), dim3(kBlockThreads), [&] { k_grad(in, th_pad, out, (size_t)n * n, g, ph); });
+    emu::launch(sgrid(n, rs), dim3(kBlockThreads), [&] { k_grad<false>(in, th_pad, out, (size_t)n * n, g, ph); });
   }
 }
 
@@ -162,14 +162,14 @@ void emu_transfer(int what, int nf, const double* in_, double* out) {
   const int nc = nf / 2;
   if (what == 0) {
     const VecIn v = whole_grid_view(in_, nf);
-    emu::launch(dim3((nc + 127) / 128, nc), dim3(128), [&] { k_restrict_F(v, out, nf, nf); });
+    emu::launch(dim3((nc + 127) / 128, nc), dim3(128), [&] { k_restrict_F<false>(v, out, nf, nf); });
   } else if (what == 1) {
     const VecIn v = whole_grid_view(in_, nc);
     emu::launch(dim3((nf + 127) / 128, nf), dim3(128), [&] { k_prolong_add_F(v, out, nf, nf); });
   } else if (what == 2) {
     emu::launch(dim3((nc + 127) / 128, nc), dim3(128), [&] { k_restrict_P(in_, out, nf, nf); });
   } else {
-    emu::launch(dim3((nf + 127) / 128, nf), dim3(128), [&] { k_prolong_add_P(in_, out, nf, nf); });
+    emu::launch(dim3((nf + 127) / 128, nf), dim3(128), [&] { k_prolong_add_P<false>(in_, out, nf, nf); });
   }
 }
 
@@ -341,6 +341,112 @@ void emu_slab_fused_push_chain(int P, int n, const double* prm, const double* th
   for (int g = 0; g < P; ++g)
     for (int k = 0; k < 4; ++k)
       std::memcpy(out + (size_t)k * n * n + (size_t)g * rows * n, &xb[g][k * fs], fs * sizeof(double));
+}
+
+// The fused V-cycle kernels on DISTRIBUTED levels, P ranks emulated in one process (every kernel runs on all ranks
+// before the next starts, so all flags are set when read):
+//   push(b) -> pre-smoothing pair [IN 1: live halo of b, static halo of wd, fused push of x2]
+//           -> residual [consumes the pushed rows, STASHES them, fused push of r]
+//           -> push(e_c on the coarse slabs)
+//           -> prolongation + sweep [IN 2: x2 with its stashed halo rows, live halo of e_c, fused push of x3]
+//           -> sweep [consumes the pushed rows of x3]
+// out_x receives the assembled x4, out_r the assembled residual b - F x2.
+void emu_slab_fused_vcycle_chain(int P, int n, const double* prm, const double* theta, const double* b,
+                                 const double* wd, const double* ec, double* out_x, double* out_r, int rs, double omega) {
+  const int rows = n / P, nc = n / 2, rows_c = rows / 2;
+  const size_t fs = (size_t)rows * n, fsc = (size_t)rows_c * nc, area = (size_t)5 * n;
+  const size_t comm_bytes = kFlagBytes + 4 * area * sizeof(double);
+  std::vector<std::vector<char>> comm(P, std::vector<char>(comm_bytes, 0));
+  std::vector<unsigned long long> dseq(P, 0ull);
+  std::vector<std::vector<unsigned int>> counter(P, std::vector<unsigned int>(8, 0u));
+  auto slab = [&](const double* g, int g_n, int g_rows, int rank) {
+    const size_t f = (size_t)g_rows * g_n;
+    std::vector<double> v(4 * f);
+    for (int k = 0; k < 4; ++k)
+      std::memcpy(&v[k * f], g + (size_t)k * g_n * g_n + (size_t)rank * g_rows * g_n, f * sizeof(double));
+    return v;
+  };
+  std::vector<std::vector<double>> bs(P), ws(P), es(P), x2(P), rr(P), x3(P), x4(P), thp(P), wdh(P), stash(P);
+  std::vector<Tables> tabs(P);
+  for (int g = 0; g < P; ++g) {
+    bs[g] = slab(b, n, rows, g);
+    ws[g] = slab(wd, n, rows, g);
+    es[g] = slab(ec, nc, rows_c, g);
+    x2[g].assign(4 * fs, 0.0); rr[g].assign(4 * fs, 0.0); x3[g].assign(4 * fs, 0.0); x4[g].assign(4 * fs, 0.0);
+    stash[g].assign(2 * 5 * n, 0.0);
+    thp[g].resize((size_t)(rows + 2) * n);
+    for (int r = -1; r <= rows; ++r)
+      std::memcpy(&thp[g][(size_t)(r + 1) * n], theta + (size_t)(((g * rows + r) % n + n) % n) * n, n * sizeof(double));
+    wdh[g].resize(2 * 4 * n);  // the neighbours' boundary rows of wd (fetched once at plan creation in plan.cu)
+    for (int k = 0; k < 4; ++k) {
+      const int rt = ((g * rows - 1) % n + n) % n, rb = ((g + 1) * rows) % n;
+      std::memcpy(&wdh[g][k * n], wd + (size_t)k * n * n + (size_t)rt * n, n * sizeof(double));
+      std::memcpy(&wdh[g][(4 + k) * n], wd + (size_t)k * n * n + (size_t)rb * n, n * sizeof(double));
+    }
+  }
+  const dim3 grid((n + kWarpCols * kBlockWarps - 1) / (kWarpCols * kBlockWarps), (rows + rs - 1) / rs);
+  auto live = [&](int g, const double* x, size_t f, int hs) {
+    VecIn in{};
+    in.x = x; in.fs = f; in.hs = hs; in.dseq = &dseq[g]; in.comm = comm[g].data(); in.area = area;
+    return in;
+  };
+  auto base = [&](int g) {
+    StokesArgs a{};
+    a.th = thp[g].data();
+    a.ph = make_phys(n, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], prm[6], 1, tabs[g]);
+    a.g = Geo{n, rows, g * rows, rs, 3};
+    a.omega = omega;
+    const int prev = (g + P - 1) % P, next = (g + 1) % P;
+    a.po = PushOut{comm[prev].data(), comm[next].data(), comm[g].data(), area, &dseq[g], &counter[g][4]};
+    return a;
+  };
+  auto push = [&](std::vector<std::vector<double>>& xs, size_t f, int r_, int n_) {
+    for (int g = 0; g < P; ++g) {
+      const int prev = (g + P - 1) % P, next = (g + 1) % P;
+      emu::launch(dim3((4 * n_ + 255) / 256), dim3(256), [&] {
+        k_halo_push(xs[g].data(), 4, f, r_, n_, comm[prev].data(), comm[next].data(), comm[g].data(), area, &dseq[g],
+                    &counter[g][0]);
+      });
+    }
+  };
+  push(bs, fs, rows, n);
+  for (int g = 0; g < P; ++g) {  // pre-smoothing pair
+    StokesArgs a = base(g);
+    a.xin = live(g, bs[g].data(), fs, n);
+    a.wd.x = ws[g].data(); a.wd.fs = fs; a.wd.hs = n; a.wd.top = wdh[g].data(); a.wd.bot = wdh[g].data() + 4 * n;
+    a.y = x2[g].data();
+    emu::launch(grid, dim3(kBlockThreads), [&] { k_stokes_x<1, 2, false, 0, true, 0>(a); });
+  }
+  for (int g = 0; g < P; ++g) {  // residual, stashing the halo rows of x2
+    StokesArgs a = base(g);
+    a.xin = live(g, x2[g].data(), fs, n);
+    a.b = bs[g].data();
+    a.y = rr[g].data();
+    a.stash = stash[g].data();
+    emu::launch(grid, dim3(kBlockThreads), [&] { k_stokes_x<0, 1, false, 0, true, 0>(a); });
+  }
+  push(es, fsc, rows_c, nc);
+  for (int g = 0; g < P; ++g) {  // prolongation + first post-sweep
+    StokesArgs a = base(g);
+    a.xin.x = x2[g].data(); a.xin.fs = fs; a.xin.hs = n; a.xin.top = stash[g].data(); a.xin.bot = stash[g].data() + 5 * n;
+    a.cin = live(g, es[g].data(), fsc, nc);
+    a.nc = nc; a.rows_c = rows_c;
+    a.b = bs[g].data();
+    a.y = x3[g].data();
+    emu::launch(grid, dim3(kBlockThreads), [&] { k_stokes_x<2, 2, false, 0, true, 0>(a); });
+  }
+  for (int g = 0; g < P; ++g) {  // second post-sweep
+    StokesArgs a = base(g);
+    a.xin = live(g, x3[g].data(), fs, n);
+    a.b = bs[g].data();
+    a.y = x4[g].data();
+    emu::launch(grid, dim3(kBlockThreads), [&] { k_stokes_x<0, 2, false, 0, false, 0>(a); });
+  }
+  for (int g = 0; g < P; ++g)
+    for (int k = 0; k < 4; ++k) {
+      std::memcpy(out_x + (size_t)k * n * n + (size_t)g * rows * n, &x4[g][k * fs], fs * sizeof(double));
+      std::memcpy(out_r + (size_t)k * n * n + (size_t)g * rows * n, &rr[g][k * fs], fs * sizeof(double));
+    }
 }
 
 }  // extern "C"

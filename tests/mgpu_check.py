@@ -78,29 +78,44 @@ def main():
     u1, b1 = manufactured_device(A1.plan)
     ud, bd = manufactured_device(p)
     report("manufactured_rhs", rel(bd, scatter_slab(b1, n, 5, rank, world)), 1e-15)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import hist_check
+
     def krylov_pair(tag, eta, A1_, M1_, Ad_, Md_, b1_, bd_, sides):
-        # conditioning of the history: the same single-GPU solve with a different (still deterministic)
-        # summation order in the dot products -- the only arithmetic difference a slab run introduces
-        os.environ["MPBP_RED_BLOCKS"] = "211"
-        bps = mp.MultiphaseBlockPreconditioner(n, xi, eta, eta_s, sub_solver=sub)
-        As, Ms = bps.get_big_A_matrix(c, d)[0], bps.approx_schur_operator(c, d)
+        # conditioning of the history: the same single-GPU solve with other (still deterministic) summation orders in
+        # the dot products -- the only arithmetic difference a slab run introduces.  Envelope over four of them.
+        variants = []
+        for rb in ("211", "307", "401", "593"):
+            os.environ["MPBP_RED_BLOCKS"] = rb
+            bps = mp.MultiphaseBlockPreconditioner(n, xi, eta, eta_s, sub_solver=sub)
+            variants.append((bps.get_big_A_matrix(c, d)[0], bps.approx_schur_operator(c, d)))
         del os.environ["MPBP_RED_BLOCKS"]
         for side, name in sides:
             mi = 60 if side == SIDE_RIGHT else 5
             xa, ia, ha = _krylov(A1_, b1_, M1_, None, 1e-8, 30, mi, side)
             xb, ib, hb = _krylov(Ad_, bd_, Md_, None, 1e-8, 30, mi, side)
-            xs_, is_, hs_ = _krylov(As, b1_, Ms, None, 1e-8, 30, mi, side)
-            k = min(len(ha), len(hb), len(hs_))
-            sens = np.abs(ha[:k] - hs_[:k]) / ha[:k]
-            allowed = np.maximum(1e-9, 1e3 * sens)
-            dev = np.abs(ha[:k] - hb[:k]) / ha[:k]
-            if rank == 0:
-                print(f"   {tag}{name}: its 1gpu/slab/1gpu' = {len(ha)}/{len(hb)}/{len(hs_)}, max rel dev {dev.max():.2e}, "
-                      f"max 1-GPU reorder sensitivity {sens.max():.2e}, info {ia}/{ib}", flush=True)
-            report(f"{tag}{name}_iterations(|d|<=1+|d_reorder|)", float(abs(len(ha) - len(hb))), 1.5 + abs(len(ha) - len(hs_)))
-            report(f"{tag}{name}_history_vs_conditioning", float((dev / allowed).max()), 1.0)
+            env = np.zeros(len(ha))
+            xdev = 0.0
+            for As, Ms in variants:
+                xs_, is_, hs_ = _krylov(As, b1_, Ms, None, 1e-8, 30, mi, side)
+                k = min(len(ha), len(hs_))
+                env[:k] = np.maximum(env[:k], np.abs(ha[:k] - hs_[:k]) / ha[:k])
+                if len(hs_) != len(ha):
+                    env[k:] = np.inf
+                xdev = max(xdev, rel(xs_, xa))
+            good = 1.0
+            try:
+                if rank == 0:
+                    hist_check(hb, ha, env, label=f"{tag}{name} slab vs single GPU")
+                else:
+                    hist_check(hb, ha, env, verbose=False)
+            except AssertionError as exc:
+                good = 0.0
+                if rank == 0:
+                    print("   " + str(exc)[:400], flush=True)
+            report(f"{tag}{name}_history (1e-10 rel, 10x reorder envelope, +-1 iteration)", 1.0 - good, 0.5)
             report(f"{tag}{name}_same_info", float(abs(ia - ib)), 0.5)
-            xtol = max(1e-6, 1e3 * rel(xs_, xa))
+            xtol = max(1e-6, 1e1 * xdev)
             report(f"{tag}{name}_solution", rel(xb, scatter_slab(xa, n, 5, rank, world)), xtol)
 
     # eta_n = 100: right-preconditioned FGMRES (the left-preconditioned history is ill conditioned at this
