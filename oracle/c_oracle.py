@@ -40,6 +40,7 @@ def load():
         lib.oc_num_threads.restype = C.c_int
         lib.oc_set_num_threads.argtypes = [C.c_int]
         lib.oc_set_noise.argtypes = [C.c_double, C.c_ulonglong]
+        lib.oc_set_form.argtypes = [C.c_int]
         for name in ("oc_apply_A", "oc_apply_F", "oc_apply_G", "oc_apply_D", "oc_apply_GtG", "oc_precond"):
             getattr(lib, name).argtypes = [C.c_void_p, _dp, _dp]
         lib.oc_vcycle.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
@@ -60,6 +61,11 @@ def set_threads(t=None):
 def set_noise(amp=0.0, seed=0):
     """Conditioning probe: ~amp relative noise on b and on every A.x / M.v inside COracle.fgmres (0 = off)."""
     load().oc_set_noise(float(amp), int(seed))
+
+
+def set_form(form=0):
+    """0: the reference's coefficient table (default); 1: the same rows evaluated differences-first (flux form)."""
+    load().oc_set_form(int(form))
 
 
 def _p(a):

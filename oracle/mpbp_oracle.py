@@ -267,11 +267,12 @@ def jacobi(A, b, N, x, omega=1.0):
 
     omega=1 is algebraically the reference's x <- (b - R x)/D.
     """
-    A = sp.csr_matrix(A)
+    if not sp.issparse(A):
+        A = sp.csr_matrix(A)
     dg = A.diagonal()
     x = np.array(x, dtype=np.float64, copy=True)
     for _ in range(N):
-        x = x + omega * (b - A @ x) / dg
+        x = x + omega * (b - mv(A, x)) / dg
     return x
 
 
@@ -335,6 +336,38 @@ class _Level:
     pass
 
 
+# ----------------------------------------------------------------------------------------------
+# rounding model for the conditioning envelopes of the residual-history tests (tests/golden/make_golden.py)
+# ----------------------------------------------------------------------------------------------
+# Any correct fp64 evaluation of a stencil row y_i = sum_j a_ij x_j satisfies |fl(y_i) - y_i| <= k u sum_j |a_ij||x_j|
+# (the standard backward-error bound); HOW the error is distributed depends on the evaluation order -- this oracle
+# sums coefficient x value terms (large cancellation on smooth fields), the CUDA kernels difference first (flux
+# form).  With the model switched on, every sparse mat-vec of the sub-solvers returns
+# y_i + amp * sqrt(k_i) * (|A| |x|)_i * N(0,1), k_i = number of terms of row i (the root-sum-square of k_i independent
+# unit-roundoff errors, the usual probabilistic refinement of the k u bound): the set of results a correct
+# implementation with another evaluation order may return.
+_ROUND = {"amp": 0.0, "rng": None, "abs": {}}
+
+
+def set_rounding_model(amp=0.0, seed=0):
+    _ROUND["amp"] = float(amp)
+    _ROUND["rng"] = np.random.default_rng(seed) if amp > 0 else None
+
+
+def mv(A, x):
+    """A @ x, plus the rounding model's perturbation when it is switched on (sparse A only)."""
+    y = A @ x
+    if _ROUND["amp"] > 0.0 and sp.issparse(A):
+        key = id(A)
+        ent = _ROUND["abs"].get(key)
+        if ent is None or ent[0] is not A:
+            Ac = A.tocsr()
+            ent = (A, abs(Ac), np.sqrt(np.maximum(np.diff(Ac.indptr), 1).astype(np.float64)))
+            _ROUND["abs"][key] = ent
+        y = y + _ROUND["amp"] * ent[2] * (ent[1] @ np.abs(x)) * _ROUND["rng"].standard_normal(len(y))
+    return y
+
+
 class Multigrid:
     """Rediscretised geometric multigrid for F (4N unknowns) and GtG (N unknowns)."""
 
@@ -381,8 +414,8 @@ class Multigrid:
             return (lv.Finv if which == "F" else lv.Pinv) @ b
         x = cfg.omega * b / dg
         for _ in range(cfg.nu1 - 1):
-            x = x + cfg.omega * (b - A @ x) / dg
-        r = b - A @ x
+            x = x + cfg.omega * (b - mv(A, x)) / dg
+        r = b - mv(A, x)
         n = lv.n
         if which == "F":
             rc = self._rF(r, n)
@@ -394,7 +427,7 @@ class Multigrid:
         else:
             x = x + prolong_cell(ec.reshape(n // 2, n // 2)).ravel()
         for _ in range(cfg.nu2):
-            x = x + cfg.omega * (b - A @ x) / dg
+            x = x + cfg.omega * (b - mv(A, x)) / dg
         return x
 
     def solve(self, which, b):
@@ -404,7 +437,7 @@ class Multigrid:
         if not cfg.cheb:
             x = self._vcycle(which, 0, b)
             for _ in range(cfg.cycles - 1):
-                x = x + self._vcycle(which, 0, b - A @ x)
+                x = x + self._vcycle(which, 0, b - mv(A, x))
         else:
             # Chebyshev iteration on B A with spectrum in [lmin, lmax] (B = one V-cycle), k = cycles steps
             lmin, lmax = cfg.lmin, cfg.lmax
@@ -415,7 +448,7 @@ class Multigrid:
             dvec = z / th
             x = dvec.copy()
             for _ in range(cfg.cycles - 1):
-                z = self._vcycle(which, 0, b - A @ x)
+                z = self._vcycle(which, 0, b - mv(A, x))
                 rho_n = 1.0 / (2.0 * sig - rho_k)
                 dvec = rho_n * rho_k * dvec + (2.0 * rho_n / de) * z
                 x = x + dvec
@@ -469,11 +502,11 @@ class ApproxSchur:
         o = self.ops
         nF = o.F.shape[1]
         Finv_v = self.F_inv @ v[:nF]  # :258
-        rhs = o.D @ Finv_v + v[nF:]  # :259
+        rhs = mv(o.D, Finv_v) + v[nF:]  # :259
         x_a = self.P_inv @ rhs  # :265
-        x_b = o.GtFG @ x_a  # :267
+        x_b = mv(o.GtFG, x_a)  # :267
         x_p = self.P_inv @ x_b  # :271
-        G_xp = o.G @ x_p  # :273
+        G_xp = mv(o.G, x_p)  # :273
         Finv_G = self.F_inv @ G_xp  # :274
         return np.concatenate([Finv_v - Finv_G, x_p])  # :275-276
 

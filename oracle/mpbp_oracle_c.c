@@ -87,6 +87,32 @@ static inline double L_v(const oc_level* L, int s, const double* u, const double
          (tN + tC + nL + nR) * v[IX(i.r, i.c)] + (nL - tC) * u[IX(i.r, i.c)] + (tC - nR) * u[IX(i.r, i.cp)] +
          (tN - nL) * u[IX(i.rm, i.c)] + (nR - tN) * u[IX(i.rm, i.cp)];
 }
+/* The same two rows evaluated differences-first (stress-divergence form): algebraically identical to the table above,
+ * but the rounding error is relative to the DIFFERENCES of neighbouring values, not to the values -- on smooth fields
+ * orders of magnitude smaller.  Selected with oc_set_form(1); used to measure how much of a residual history is an
+ * artefact of the evaluation order (tests/golden/make_large.py), never as the reference definition.
+ *   Q[r,c] = th[r,c]   ((u[r,c+1]-u[r,c]) + (v[r+1,c]-v[r,c]))     T[r,c] = node[r,c] ((u[r-1,c]-u[r,c]) + (v[r,c]-v[r,c-1]))
+ *   (L u)_u = (Q[r,c]-Q[r,c-1]) + (T[r,c]-T[r+1,c])                (L u)_v = (T[r,c+1]-T[r,c]) + (Q[r,c]-Q[r-1,c])      */
+static int g_form = 0;
+void oc_set_form(int f) { g_form = f; }
+static inline double L_u_flux(const oc_level* L, int s, const double* u, const double* v, oc_idx i) {
+  const int n = L->n;
+  const double* th = L->theta;
+  const double Qc = ph(th[IX(i.r, i.c)], s) * ((u[IX(i.r, i.cp)] - u[IX(i.r, i.c)]) + (v[IX(i.rp, i.c)] - v[IX(i.r, i.c)]));
+  const double Qw = ph(th[IX(i.r, i.cm)], s) * ((u[IX(i.r, i.c)] - u[IX(i.r, i.cm)]) + (v[IX(i.rp, i.cm)] - v[IX(i.r, i.cm)]));
+  const double Tc = ph(L->node[IX(i.r, i.c)], s) * ((u[IX(i.rm, i.c)] - u[IX(i.r, i.c)]) + (v[IX(i.r, i.c)] - v[IX(i.r, i.cm)]));
+  const double Ts = ph(L->node[IX(i.rp, i.c)], s) * ((u[IX(i.r, i.c)] - u[IX(i.rp, i.c)]) + (v[IX(i.rp, i.c)] - v[IX(i.rp, i.cm)]));
+  return (Qc - Qw) + (Tc - Ts);
+}
+static inline double L_v_flux(const oc_level* L, int s, const double* u, const double* v, oc_idx i) {
+  const int n = L->n;
+  const double* th = L->theta;
+  const double Te = ph(L->node[IX(i.r, i.cp)], s) * ((u[IX(i.rm, i.cp)] - u[IX(i.r, i.cp)]) + (v[IX(i.r, i.cp)] - v[IX(i.r, i.c)]));
+  const double Tc = ph(L->node[IX(i.r, i.c)], s) * ((u[IX(i.rm, i.c)] - u[IX(i.r, i.c)]) + (v[IX(i.r, i.c)] - v[IX(i.r, i.cm)]));
+  const double Qc = ph(th[IX(i.r, i.c)], s) * ((u[IX(i.r, i.cp)] - u[IX(i.r, i.c)]) + (v[IX(i.rp, i.c)] - v[IX(i.r, i.c)]));
+  const double Qn = ph(th[IX(i.rm, i.c)], s) * ((u[IX(i.rm, i.cp)] - u[IX(i.rm, i.c)]) + (v[IX(i.r, i.c)] - v[IX(i.rm, i.c)]));
+  return (Te - Tc) + (Qc - Qn);
+}
 static inline double L_u_diag(const oc_level* L, int s, oc_idx i) {
   const int n = L->n;
   return -(ph(L->theta[IX(i.r, i.c)], s) + ph(L->theta[IX(i.r, i.cm)], s) + ph(L->node[IX(i.r, i.c)], s) +
@@ -122,10 +148,19 @@ static void stokes_op(const oc_ctx* C, const oc_level* L, int mode, int with_p, 
       const double mu = L->mass_u[k], mv = L->mass_v[k];  /* :325-326 */
       const double d = C->d_u;
       /* F = XI_block + d_u * blockdiag(eta_n L_n, eta_s L_s), :331-337 */
-      double y_un = (C->c * mu - d * Xu) * un[k] + d * Xu * us[k] + d * C->eta_n * ih2 * L_u(L, 0, un, vn, ix);
-      double y_vn = (C->c * mv - d * Xv) * vn[k] + d * Xv * vs[k] + d * C->eta_n * ih2 * L_v(L, 0, un, vn, ix);
-      double y_us = (C->c * (1.0 - mu) - d * Xu) * us[k] + d * Xu * un[k] + d * C->eta_s * ih2 * L_u(L, 1, us, vs, ix);
-      double y_vs = (C->c * (1.0 - mv) - d * Xv) * vs[k] + d * Xv * vn[k] + d * C->eta_s * ih2 * L_v(L, 1, us, vs, ix);
+      double y_un, y_vn, y_us, y_vs;
+      if (g_form == 0) {
+        y_un = (C->c * mu - d * Xu) * un[k] + d * Xu * us[k] + d * C->eta_n * ih2 * L_u(L, 0, un, vn, ix);
+        y_vn = (C->c * mv - d * Xv) * vn[k] + d * Xv * vs[k] + d * C->eta_n * ih2 * L_v(L, 0, un, vn, ix);
+        y_us = (C->c * (1.0 - mu) - d * Xu) * us[k] + d * Xu * un[k] + d * C->eta_s * ih2 * L_u(L, 1, us, vs, ix);
+        y_vs = (C->c * (1.0 - mv) - d * Xv) * vs[k] + d * Xv * vn[k] + d * C->eta_s * ih2 * L_v(L, 1, us, vs, ix);
+      } else {
+        const double du = un[k] - us[k], dv = vn[k] - vs[k];
+        y_un = C->c * mu * un[k] - d * Xu * du + d * C->eta_n * ih2 * L_u_flux(L, 0, un, vn, ix);
+        y_vn = C->c * mv * vn[k] - d * Xv * dv + d * C->eta_n * ih2 * L_v_flux(L, 0, un, vn, ix);
+        y_us = C->c * (1.0 - mu) * us[k] + d * Xu * du + d * C->eta_s * ih2 * L_u_flux(L, 1, us, vs, ix);
+        y_vs = C->c * (1.0 - mv) * vs[k] + d * Xv * dv + d * C->eta_s * ih2 * L_v_flux(L, 1, us, vs, ix);
+      }
       if (with_p) {
         const double gx = C->d_p * ih * (p[k] - p[IX(r, ix.cm)]);  /* :204-210 */
         const double gy = C->d_p * ih * (p[IX(ix.rm, c)] - p[k]);  /* :213-219 */

@@ -23,8 +23,8 @@ def test_criterion_accepts_independent_implementation_and_rejects_wrong_historie
     _, info, h = co.fgmres(g["b_vec"], tol=1e-8, restart=150, maxiter=150)
     c_oracle.set_threads()
     assert info == 0
-    worst, n_ill = hist_check(h, g["hist"], g["hist_sens"], label=f"C oracle vs {fx}")
-    assert n_ill <= 3  # the ill-conditioned (plateau) entries are a small minority
+    worst, kstar = hist_check(h, g["hist"], g["hist_sens"], label=f"C oracle vs {fx}")
+    assert kstar >= 6  # the reproducible prefix (held to 10 x the oracle's own scatter) is never trivial
     for wrong in (h * 1.5, np.concatenate([h[:1], h[:-1]]), np.concatenate([h[:2], h[:-2]]), h[:-2]):
         with pytest.raises(AssertionError):
             hist_check(wrong, g["hist"], g["hist_sens"], verbose=False)
@@ -34,4 +34,4 @@ def test_envelopes_have_sixteen_runs_and_strict_entries():
     """Where the oracle's history is reproducible (Jacobi sub-solves, eta=1) the criterion is the plain 1e-10."""
     for fx in ("solve_jacobi_n16_eta100.npz", "solve_mgcheb_n32_eta1.npz"):
         env = golden(fx)["hist_sens"]
-        assert np.isfinite(env).all() and env.max() < 1e-9
+        assert np.isfinite(env).all() and env.max() < 1e-8
