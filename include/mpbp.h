@@ -115,6 +115,9 @@ int mpbp_solve_P(mpbp_plan*, const double* b, double* x, void* stream);
 int mpbp_precond_apply(mpbp_plan*, const double* v, double* z, void* stream);
 /* same with HOST buffers (h2d + apply + d2h inside the call): what LinearOperator.matvec sees, solve.py:280-281 */
 int mpbp_precond_apply_host(mpbp_plan*, const double* v_host, double* z_host, void* stream);
+/* communication probe for the multi-GPU throughput sweep (BASELINE.json configs[4]: "halo + allreduce scaling"): average
+ * microseconds of one level-0 halo exchange of a 5-field vector and of one scalar all-reduce (0 with one rank) */
+int mpbp_comm_probe(mpbp_plan*, int reps, double* halo_us, double* allreduce_us, void* stream);
 /* algorithmic bytes of one precond apply / one A apply under the current configuration (SURVEY 8d accounting) */
 int mpbp_precond_bytes(const mpbp_plan*, double* bytes);
 
@@ -144,6 +147,13 @@ typedef struct mpbp_gmres_opts {
   int force_iters;   /* >0: ignore convergence and run exactly this many inner iterations (benchmarking) */
   void* workspace;   /* optional caller-owned device memory for the Krylov bases */
   size_t workspace_bytes;
+  /* per-iteration callback of pyamg's fgmres as the reference uses it, callback=print_true_res_norm(A, b) at
+   * solve.py:285 / :163-169: after every inner iteration the current iterate x_k = x0 + Z y_k is formed in xk_buf
+   * (DEVICE, 5N doubles, caller-owned; one multi-axpy, no extra preconditioner apply), the stream is synchronised and
+   * iter_cb(cb_user, k, relative recurrence residual) is called; a non-zero return stops the solve.  RIGHT side only. */
+  void* xk_buf;
+  int (*iter_cb)(void* cb_user, int iteration, double rel_residual);
+  void* cb_user;
 } mpbp_gmres_opts;
 int mpbp_gmres_opts_default(mpbp_gmres_opts*);
 int mpbp_gmres_workspace_bytes(const mpbp_plan*, const mpbp_gmres_opts*, size_t* bytes);
@@ -151,6 +161,12 @@ int mpbp_gmres_workspace_bytes(const mpbp_plan*, const mpbp_gmres_opts*, size_t*
  * *info: 0 converged, >0 = maxiter reached (scipy semantics) */
 int mpbp_gmres(mpbp_plan*, const double* b, double* x, const mpbp_gmres_opts*, double* hist_host, int hist_cap,
                int* n_iters, int* info, void* stream);
+/* Spectral diagnostics as a by-product of the solve (replaces the dense compute_preconditioned_A + PETSc/SLEPc
+ * get_eigenvals analysis of solve.py:103-200, :304-309): the upper Hessenberg matrix H_k = V_{k+1}^T (A M^-1) V_k
+ * (RIGHT; M A for LEFT) of the LAST Arnoldi cycle of the last mpbp_gmres call on this plan, before the Givens
+ * rotations.  Written row-major into H ((k+1) x k, leading dimension ldh >= k); *k receives the cycle length.
+ * Its eigenvalues (Ritz values) approximate the outer spectrum of the preconditioned operator. */
+int mpbp_gmres_last_hessenberg(const mpbp_plan*, double* H_host, int ldh, int* k);
 /* HOST b in, HOST x out: what `fgmres(A, b_vec, M=...)` is to the reference's caller */
 int mpbp_gmres_host(mpbp_plan*, const double* b_host, double* x_host, const mpbp_gmres_opts*, double* hist_host,
                     int hist_cap, int* n_iters, int* info, void* stream);

@@ -7,6 +7,7 @@ layout: preconditioner.py, solve.py, apply.py, utils.py.
 from ._cabi import MpbpError, SIDE_LEFT, SIDE_RIGHT  # noqa: F401
 from .preconditioner import (ApproxSchurOperator, MultiphaseBlockPreconditioner, Plan, SubSolver,  # noqa: F401
                              SystemOperator, thn, ths)
-from .solve import (Jacobi, fgmres, gmres, main, print_true_res_norm, solve_with_approx_schur_pc,  # noqa: F401
-                    solve_without_pc)
-from .utils import fill_sol_and_RHS_vecs, max_norm, print_norms, weighted_L1, weighted_L2  # noqa: F401
+from .solve import (Jacobi, fgmres, gmres, last_hessenberg, main, print_true_res_norm,  # noqa: F401
+                    solve_with_approx_schur_pc, solve_with_exact_schur_pc, solve_without_pc, spectral_diagnostics)
+from .utils import (check_individual_operators, fill_sol_and_RHS_vecs, max_norm, print_norms,  # noqa: F401
+                    weighted_L1, weighted_L2)

@@ -54,8 +54,13 @@ class GmresOpts(C.Structure):
         ("force_iters", C.c_int),
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_size_t),
+        ("xk_buf", C.c_void_p),
+        ("iter_cb", C.c_void_p),
+        ("cb_user", C.c_void_p),
     ]
 
+
+ITER_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_double)
 
 _P = C.c_void_p  # plan handle / device pointer / stream
 _D = C.c_void_p
@@ -87,6 +92,7 @@ SIGNATURES = {
     "mpbp_precond_apply": (C.c_int, [_P, _D, _D, _P]),
     "mpbp_precond_apply_host": (C.c_int, [_P, C.c_void_p, C.c_void_p, _P]),
     "mpbp_precond_bytes": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "mpbp_comm_probe": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), _P]),
     "mpbp_dot": (C.c_int, [_P, _D, _D, C.c_size_t, C.POINTER(C.c_double), _P]),
     "mpbp_nrm2": (C.c_int, [_P, _D, C.c_size_t, C.POINTER(C.c_double), _P]),
     "mpbp_axpy": (C.c_int, [_P, C.c_double, _D, _D, C.c_size_t, _P]),
@@ -98,6 +104,7 @@ SIGNATURES = {
     "mpbp_gmres_workspace_bytes": (C.c_int, [_P, C.POINTER(GmresOpts), C.POINTER(C.c_size_t)]),
     "mpbp_gmres": (C.c_int, [_P, _D, _D, C.POINTER(GmresOpts), C.POINTER(C.c_double), C.c_int,
                              C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
+    "mpbp_gmres_last_hessenberg": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]),
     "mpbp_gmres_host": (C.c_int, [_P, C.c_void_p, C.c_void_p, C.POINTER(GmresOpts), C.POINTER(C.c_double), C.c_int,
                                   C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
 }

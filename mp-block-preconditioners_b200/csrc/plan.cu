@@ -139,6 +139,8 @@ struct mpbp_plan {
   size_t comm_area = 0;                     // doubles per (slot, direction) halo area
   unsigned long long* dseq = nullptr;       // device-resident exchange counter (identical on all ranks)
   std::vector<char*> comm_all;              // every rank's comm buffer mapped here (index = rank; own = comm_local)
+  std::vector<double> last_H;               // un-rotated Hessenberg of the last Arnoldi cycle, (last_m+1) x last_m row-major
+  int last_m = 0, last_k = 0;               // allocated / used cycle length
   RedCtx red{};                             // peer-memory all-reduce of the reduction kernels (nranks <= 1: off)
 };
 
@@ -1561,6 +1563,54 @@ extern "C" int mpbp_precond_apply(mpbp_plan* p, const double* v, double* z, void
   return leave(p, body());
 }
 
+// Communication probe (bench.py --workload apply8192): average time of one level-0 halo exchange of a 5-field vector
+// (push + a consumer that only waits) and of one scalar all-reduce, in microseconds, measured with CUDA events.
+extern "C" int mpbp_comm_probe(mpbp_plan* p, int reps, double* halo_us, double* allreduce_us, void* stream) {
+  ENTER(p, stream);
+  auto body = [&]() -> int {
+    if (!halo_us || !allreduce_us || reps < 1) return set_err(MPBP_E_ARG, "comm_probe: bad arguments");
+    *halo_us = *allreduce_us = 0.0;
+    if (p->nranks == 1) return 0;
+    Level& v = p->lev[0];
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    float ms = 0.f;
+    for (int pass = 0; pass < 2; ++pass) {  // pass 0: warm-up
+      CU(cudaEventRecord(e0, p->st));
+      for (int i = 0; i < reps; ++i) {
+        VecIn in{};
+        p->pending_push = nullptr;
+        RET(make_view(p, v, p->vin, 5, in));
+        if (p->p2p) {
+          k_halo_consume<<<1, 32, 0, p->st>>>(in, p->scal + kScal - 2);
+          LAUNCH_CHECK(p);
+        }
+      }
+      CU(cudaEventRecord(e1, p->st));
+      CU(cudaEventSynchronize(e1));
+      CU(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    *halo_us = 1e3 * ms / reps;
+    for (int pass = 0; pass < 2; ++pass) {
+      CU(cudaEventRecord(e0, p->st));
+      for (int i = 0; i < reps; ++i) {
+        k_sum<<<1, kRedThreads, 0, p->st>>>(p->vin, 1024, p->partial, p->counter, p->scal + kScal - 2, p->red);
+        LAUNCH_CHECK(p);
+        if (p->red.nranks <= 1) RET(allreduce_scal(p, p->scal + kScal - 2, 1));
+      }
+      CU(cudaEventRecord(e1, p->st));
+      CU(cudaEventSynchronize(e1));
+      CU(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    *allreduce_us = 1e3 * ms / reps;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return 0;
+  };
+  return leave(p, body());
+}
+
 static int ensure_hostbuf(mpbp_plan* p) {
   const size_t bytes = 5 * p->lev[0].fs() * sizeof(double);
   for (int i = 0; i < 2; ++i)
@@ -1803,6 +1853,9 @@ static int gmres_left(mpbp_plan* p, const double* b, double* x, const mpbp_gmres
   double presid = 0.0, rnorm = 0.0;
   std::vector<double> H((size_t)m * (m + 1), 0.0), giv((size_t)m * 2, 0.0), S(m + 1), yv(m);
   double* r = tmp;  // residual lives in tmp between outer iterations
+  p->last_H.assign((size_t)(m + 1) * m, 0.0);
+  p->last_m = m;
+  p->last_k = 0;
 
   for (int iteration = 0; iteration < o->maxiter; ++iteration) {
     if (iteration == 0) {
@@ -1839,6 +1892,9 @@ static int gmres_left(mpbp_plan* p, const double* b, double* x, const mpbp_gmres
       double* h = &H[(size_t)col * (m + 1)];
       for (int k = 0; k <= col; ++k) h[k] = hs[1 + k];
       h[col + 1] = h1;
+      if (col == 0) std::fill(p->last_H.begin(), p->last_H.end(), 0.0);
+      for (int k = 0; k <= col + 1; ++k) p->last_H[(size_t)k * m + col] = hs[1 + k];
+      p->last_k = col + 1;
       if (h1 <= eps * h0) {
         h[col + 1] = 0.0;
         breakdown = true;
@@ -1923,9 +1979,13 @@ static int gmres_right(mpbp_plan* p, const double* b, double* x, const mpbp_gmre
   if (!o->x0_nonzero) CU(cudaMemsetAsync(x, 0, len * sizeof(double), p->st));
   std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), gv(m + 1), yv(m);
   auto Hm = [&](int i, int j) -> double& { return H[(size_t)i * m + j]; };
+  p->last_H.assign((size_t)(m + 1) * m, 0.0);
+  p->last_m = m;
+  p->last_k = 0;
   int it = 0;
   bool first = true;
-  while (it < maxit) {
+  bool stop = false;
+  while (it < maxit && !stop) {
     if (first && !o->x0_nonzero) {
       RET(v_copy(p, b, tmp, len));
     } else {
@@ -1953,6 +2013,9 @@ static int gmres_right(mpbp_plan* p, const double* b, double* x, const mpbp_gmre
       LAUNCH_CHECK(p);
       RET(fetch_scal(p, ds, j + 2, hs));
       for (int i = 0; i <= j + 1; ++i) Hm(i, j) = hs[i];
+      if (j == 0) std::fill(p->last_H.begin(), p->last_H.end(), 0.0);
+      for (int i = 0; i <= j + 1; ++i) p->last_H[(size_t)i * m + j] = hs[i];
+      p->last_k = j + 1;
       for (int i = 0; i < j; ++i) {
         const double t = cs[i] * Hm(i, j) + sn[i] * Hm(i + 1, j);
         Hm(i + 1, j) = -sn[i] * Hm(i, j) + cs[i] * Hm(i + 1, j);
@@ -1969,7 +2032,21 @@ static int gmres_right(mpbp_plan* p, const double* b, double* x, const mpbp_gmre
       jdone = j + 1;
       res = std::fabs(gv[j + 1]);
       if (hist && it <= hist_cap) hist[it - 1] = res / bn;
-      if ((!forced && res < o->rtol * bn) || it >= maxit) break;
+      if (o->iter_cb && o->xk_buf) {
+        // the iterate of this iteration, x_k = x + Z y_k (what pyamg hands to callback=, solve.py:285): one
+        // back substitution on the host and one multi-axpy -- no extra preconditioner apply
+        for (int i = jdone - 1; i >= 0; --i) {
+          double s = gv[i];
+          for (int k = i + 1; k < jdone; ++k) s -= Hm(i, k) * yv[k];
+          yv[i] = s / Hm(i, i);
+        }
+        double* xk = (double*)o->xk_buf;
+        RET(v_copy(p, x, xk, len));
+        RET(v_multi_axpy(p, Z, len, jdone, yv.data(), xk, len));
+        CU(cudaStreamSynchronize(p->st));
+        if (o->iter_cb(o->cb_user, it, res / bn) != 0) stop = true;
+      }
+      if ((!forced && res < o->rtol * bn) || it >= maxit || stop) break;
     }
     // back substitution on the jdone x jdone triangle
     for (int i = jdone - 1; i >= 0; --i) {
@@ -2011,6 +2088,16 @@ static int gmres_dispatch(mpbp_plan* p, const double* b, double* x, const mpbp_g
   if (info) *info = inf;
   if (rc) return rc;
   CU(cudaStreamSynchronize(p->st));
+  return 0;
+}
+
+extern "C" int mpbp_gmres_last_hessenberg(const mpbp_plan* p, double* H, int ldh, int* k) {
+  if (!p || !k) return set_err(MPBP_E_ARG, "null argument");
+  *k = p->last_k;
+  if (!H) return 0;  // size query
+  if (ldh < p->last_k) return set_err(MPBP_E_ARG, "ldh=%d < cycle length %d", ldh, p->last_k);
+  for (int i = 0; i <= p->last_k; ++i)
+    for (int j = 0; j < p->last_k; ++j) H[(size_t)i * ldh + j] = p->last_H[(size_t)i * p->last_m + j];
   return 0;
 }
 

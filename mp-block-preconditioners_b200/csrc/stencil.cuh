@@ -163,6 +163,12 @@ __global__ void __launch_bounds__(256) k_halo_push(const double* __restrict__ x,
   }
 }
 
+// consumer side of one halo exchange and nothing else (communication probe: exchange latency without a stencil)
+__global__ void k_halo_consume(VecIn v, double* sink) {
+  halo_wait(v, true, true);
+  if (threadIdx.x == 0 && sink) sink[0] = v.top[0] + v.bot[0];
+}
+
 // Chebyshev epilogue of the last smoothing sweep of a V-cycle: the sweep's result is the cycle's output z, which is
 // consumed in registers instead of being stored:  d = ca*d + cb*z ;  xk += d.
 struct ChebEp {

@@ -249,15 +249,41 @@ class GtFGOperator(_Operator):
         super().__init__(plan, 1, 1)
 
 
-class ExactSchurUnsupported:
-    """Placeholder for the dense exact Schur complement S = -D F^-1 G (preconditioner.py:343-346):
-    an O(n^6) dense research cross-check that is out of scope of the hot path. Only .shape exists."""
+class ExactSchurOperator:
+    """The dense exact Schur complement S = -D F^-1 G of preconditioner.py:343-346, for SMALL grids only: it is the
+    reference's O(n^6) research cross-check (solve_with_exact_schur_pc, solve.py:210-238), kept as a verification path.
+    F, D, G are obtained by applying the GPU operators to the identity, the dense algebra (scipy.linalg.inv, as the
+    reference) runs on the host, lazily.  Above n = MAX_N only .shape exists."""
+
+    MAX_N = 24
 
     def __init__(self, plan):
+        self.plan = plan
         self.shape = (plan.n * plan.n, plan.n * plan.n)
+        self.dtype = np.dtype(np.float64)
+        self._S = None
 
-    def __matmul__(self, x):
-        raise NotImplementedError("the dense exact Schur complement is out of scope (SURVEY.md 2, 8b)")
+    def toarray(self):
+        if self._S is None:
+            p = self.plan
+            if p.n > self.MAX_N or p.nranks > 1:
+                raise NotImplementedError(f"the dense exact Schur complement is a small-n verification path (n <= {self.MAX_N}, "
+                                          "one GPU); it is O(n^6) and out of scope of the hot path (SURVEY.md 2, 8b)")
+            import scipy.linalg
+            F = VelocityOperator(p).toarray()
+            D = DivergenceOperator(p).toarray()
+            G = GradientOperator(p).toarray()
+            self._S = -1.0 * np.matmul(np.matmul(D, scipy.linalg.inv(F)), G)  # preconditioner.py:344-346
+        return self._S
+
+    def matvec(self, x):
+        return self.toarray() @ np.asarray(x, dtype=np.float64)
+
+    __matmul__ = matvec
+    dot = matvec
+
+
+ExactSchurUnsupported = ExactSchurOperator  # former name (round 1 placeholder)
 
 
 class ApproxSolve(_Operator):
@@ -341,9 +367,22 @@ class MultiphaseBlockPreconditioner:
         self._plans.clear()
 
     def get_big_A_matrix(self, c, d_u, d_p: float = 1.0, d_div: float = -1.0):
-        """(A, S, F, D, G) as at preconditioner.py:299-349; S is a placeholder (out of scope)."""
+        """(A, S, F, D, G) as at preconditioner.py:299-349; S is the lazily built dense exact Schur complement
+        (small n only, see ExactSchurOperator)."""
         p = self.plan(c, d_u, d_p, d_div)
-        return SystemOperator(p), ExactSchurUnsupported(p), VelocityOperator(p), DivergenceOperator(p), GradientOperator(p)
+        return SystemOperator(p), ExactSchurOperator(p), VelocityOperator(p), DivergenceOperator(p), GradientOperator(p)
+
+    def get_thn_vals(self, n, row_on_grid, col_on_grid, is_ths):
+        """preconditioner.py:26-84: the six cell-centred volume fractions around the u-face of cell
+        (row_on_grid, col_on_grid), periodic: (i,j), (i+1,j), (i,j+1), (i+1,j+1), (i,j-1), (i+1,j-1) in the reference's
+        naming, i.e. columns col-1 / col and rows row, row-1, row+1.  (The CUDA kernels recompute these averages in
+        registers from the cell field; this method exists for callers of the reference's API.)"""
+        dx, dy = self.dx, self.dy
+        cw, ce = (col_on_grid - 1) % n, col_on_grid % n
+        rn, rs = (row_on_grid - 1) % n, (row_on_grid + 1) % n
+        cell = lambda r, c: thn(-(r + 0.5) * dy, (c + 0.5) * dx)
+        vals = (cell(row_on_grid, cw), cell(row_on_grid, ce), cell(rn, cw), cell(rn, ce), cell(rs, cw), cell(rs, ce))
+        return tuple(1.0 - v for v in vals) if is_ths else vals
 
     def get_block_matrices(self, is_ths):
         """(L, D, XI, G) of one phase (preconditioner.py:86-297) as operator objects on 2N / N vectors."""

@@ -10,14 +10,16 @@ import ctypes as C
 import numpy as np
 import torch
 
-from ._cabi import SIDE_LEFT, SIDE_RIGHT, GmresOpts, check
+from ._cabi import ITER_CB, SIDE_LEFT, SIDE_RIGHT, GmresOpts, check
 from .preconditioner import (ApproxSchurOperator, GtGOperator, MultiphaseBlockPreconditioner, SubSolver,
                              SystemOperator, VelocityOperator)
 from .utils import PI, fill_sol_and_RHS_vecs, manufactured_device, print_norms
 
 
-def _krylov(A, b, M, x0, rtol, restart, maxiter, side, force_iters=0, host=False):
-    """One call of mpbp_gmres / mpbp_gmres_host. Returns (x, info, history ndarray)."""
+def _krylov(A, b, M, x0, rtol, restart, maxiter, side, force_iters=0, host=False, callback=None):
+    """One call of mpbp_gmres / mpbp_gmres_host. Returns (x, info, history ndarray).
+    callback(x_k) (right side only) is called after every inner iteration with the current iterate, formed on the
+    device as x0 + Z y_k (pyamg's callback semantics, solve.py:285); numpy b -> numpy x_k, torch b -> torch x_k."""
     if not isinstance(A, SystemOperator):
         raise TypeError("A must be the SystemOperator returned by get_big_A_matrix")
     if M is not None and not (isinstance(M, ApproxSchurOperator) and M.plan is A.plan):
@@ -28,8 +30,23 @@ def _krylov(A, b, M, x0, rtol, restart, maxiter, side, force_iters=0, host=False
     check(lib.mpbp_gmres_opts_default(C.byref(o)))
     o.rtol, o.restart, o.maxiter, o.side = float(rtol), int(restart), int(maxiter), int(side)
     o.use_precond = int(M is not None)
-    o.x0_nonzero = int(x0 is not None)
+    x0_nz = x0 is not None and bool((x0 != 0).any())  # a zero initial guess costs nothing extra (solve.py:205-207)
+    o.x0_nonzero = int(x0_nz)
     o.force_iters = int(force_iters)
+    keep = []
+    if callback is not None:
+        if side != SIDE_RIGHT or host:
+            raise NotImplementedError("the per-iteration iterate callback exists for the right-preconditioned device path")
+        xk_buf = torch.empty(5 * p.N, dtype=torch.float64, device=p.device)
+        as_np = not isinstance(b, torch.Tensor)
+
+        def _cb(_user, it, relres):
+            callback(xk_buf.cpu().numpy() if as_np else xk_buf.clone())
+            return 0
+        cfn = ITER_CB(_cb)
+        keep += [xk_buf, cfn]
+        o.xk_buf = C.c_void_p(xk_buf.data_ptr())
+        o.iter_cb = C.cast(cfn, C.c_void_p)
     need = C.c_size_t()
     check(lib.mpbp_gmres_workspace_bytes(p.h, C.byref(o), C.byref(need)))
     if p.kry_ws is None or p.kry_ws.numel() < need.value:
@@ -45,13 +62,13 @@ def _krylov(A, b, M, x0, rtol, restart, maxiter, side, force_iters=0, host=False
     with torch.cuda.device(p.device):
         if host:
             bh = np.ascontiguousarray(b, dtype=np.float64)
-            xh = np.zeros(length) if x0 is None else np.array(x0, dtype=np.float64, copy=True)
+            xh = np.zeros(length) if not x0_nz else np.array(x0, dtype=np.float64, copy=True)
             check(lib.mpbp_gmres_host(p.h, bh.ctypes.data_as(C.c_void_p), xh.ctypes.data_as(C.c_void_p), C.byref(o),
                                       hist, cap, C.byref(nit), C.byref(info), p.stream()))
             x = xh
         else:
             bt, was_np = p._to_dev(b, length)
-            if x0 is None:
+            if not x0_nz:
                 xt = torch.empty(length, dtype=torch.float64, device=p.device)
             else:
                 xt, _ = p._to_dev(x0, length)
@@ -67,22 +84,53 @@ def fgmres(A, b, x0=None, tol=1e-5, restart=None, maxiter=None, M=None, callback
     reference uses it (solve.py:207, :237, :285).  Returns (x, info); info 0 = converged.
 
     restart=None: one cycle of at most `maxiter` inner iterations.  `residuals` (a list) receives the
-    relative recurrence-residual history.  `callback(x_k)` is a verification mode: the iterates are
-    reproduced by re-running the (deterministic) solve truncated at k iterations, O(k^2) work.
+    relative recurrence-residual history.  `callback(x_k)` is called once per inner iteration with the current
+    iterate x_k = x0 + Z y_k (pyamg's semantics; one multi-axpy per iteration, no extra preconditioner apply).
     """
     if maxiter is None:
         maxiter = min(A.shape[0], 40)
     m = maxiter if restart is None else restart
     total = maxiter if restart is None else restart * maxiter
-    x, info, hist = _krylov(A, b, M, x0, tol, m, total, SIDE_RIGHT, host=host)
+    x, info, hist = _krylov(A, b, M, x0, tol, m, total, SIDE_RIGHT, host=host, callback=callback)
     if residuals is not None:
         residuals[:] = list(hist)
     fgmres.last_history = hist
-    if callback is not None:
-        for k in range(1, len(hist) + 1):
-            xk, _, _ = _krylov(A, b, M, x0, tol, m, total, SIDE_RIGHT, force_iters=k)
-            callback(xk)
     return x, info
+
+
+def last_hessenberg(A):
+    """(k+1) x k upper Hessenberg matrix of the last Arnoldi cycle of the last fgmres / gmres call on A's plan."""
+    p = A.plan
+    k = C.c_int(0)
+    check(p.lib.mpbp_gmres_last_hessenberg(p.h, None, 0, C.byref(k)))
+    H = np.zeros((k.value + 1, max(k.value, 1)))
+    if k.value:
+        check(p.lib.mpbp_gmres_last_hessenberg(p.h, H.ctypes.data_as(C.POINTER(C.c_double)), H.shape[1], C.byref(k)))
+    return H[:, :k.value]
+
+
+def spectral_diagnostics(A, nev=10):
+    """Replacement of the reference's dense spectrum analysis (compute_preconditioned_A + get_eigenvals / SLEPc,
+    solve.py:103-200, :304-309) as a by-product of the solve: Ritz values of the preconditioned operator A M^-1
+    (fgmres; M A for gmres) from the Hessenberg matrix of the last Arnoldi cycle.  Returns a dict with all Ritz
+    values, the `nev` largest in magnitude (what SLEPc's default EPS returns, solve.py:121), the harmonic Ritz
+    values (better for the eigenvalues closest to 0) and the spread max|theta| / min|theta|."""
+    H = last_hessenberg(A)
+    k = H.shape[1]
+    if k == 0:
+        return {"k": 0, "ritz": np.zeros(0), "largest": np.zeros(0), "harmonic": np.zeros(0), "spread": float("nan")}
+    Hk = H[:k, :k]
+    ritz = np.linalg.eigvals(Hk)
+    ek = np.zeros(k)
+    ek[-1] = 1.0
+    try:  # harmonic Ritz values: eig(H_k + h_{k+1,k}^2 H_k^{-H} e_k e_k^T)
+        f = np.linalg.solve(Hk.conj().T, ek)
+        harm = np.linalg.eigvals(Hk + (H[k, k - 1] ** 2) * np.outer(f, ek))
+    except np.linalg.LinAlgError:
+        harm = ritz
+    order = np.argsort(-np.abs(ritz))
+    return {"k": k, "ritz": ritz[order], "largest": ritz[order][:nev], "harmonic": harm[np.argsort(-np.abs(harm))],
+            "spread": float(np.abs(ritz).max() / max(np.abs(ritz).min(), 1e-300))}
 
 
 def gmres(A, b, x0=None, *, rtol=1e-5, atol=0.0, restart=None, maxiter=None, M=None, callback=None,
@@ -179,6 +227,84 @@ def solve_without_pc(n, A, b_vec, u_vec, verbose=True):
     if verbose:
         print_norms(u_approx, u_vec, 1 / n, 1 / n, n)
     return u_approx, info
+
+
+def _fgmres_host_M(A, b, M, tol, maxiter, callback=None):
+    """Right-preconditioned FGMRES for an ARBITRARY host callable M (small verification problems): A.x runs on the GPU
+    operator, the Arnoldi bookkeeping in numpy.  Same algorithm as mpbp_gmres RIGHT (MGS, Givens, one cycle)."""
+    b = np.asarray(b, dtype=np.float64)
+    m = maxiter
+    x = np.zeros_like(b)
+    bn = np.linalg.norm(b) or 1.0
+    V = np.zeros((m + 1, len(b)))
+    Z = np.zeros((m, len(b)))
+    H = np.zeros((m + 1, m))
+    cs, sn, g = np.zeros(m), np.zeros(m), np.zeros(m + 1)
+    g[0] = np.linalg.norm(b)
+    V[0] = b / g[0]
+    hist, info, jd = [], maxiter, 0
+    for j in range(m):
+        Z[j] = M(V[j])
+        w = A @ Z[j]
+        for i in range(j + 1):
+            H[i, j] = np.dot(V[i], w)
+            w = w - H[i, j] * V[i]
+        H[j + 1, j] = np.linalg.norm(w)
+        if H[j + 1, j] != 0:
+            V[j + 1] = w / H[j + 1, j]
+        for i in range(j):
+            t = cs[i] * H[i, j] + sn[i] * H[i + 1, j]
+            H[i + 1, j] = -sn[i] * H[i, j] + cs[i] * H[i + 1, j]
+            H[i, j] = t
+        den = np.hypot(H[j, j], H[j + 1, j])
+        cs[j], sn[j] = H[j, j] / den, H[j + 1, j] / den
+        H[j, j], H[j + 1, j] = den, 0.0
+        g[j + 1] = -sn[j] * g[j]
+        g[j] = cs[j] * g[j]
+        jd = j + 1
+        hist.append(abs(g[j + 1]) / bn)
+        if callback is not None:
+            callback(x + np.linalg.solve(np.triu(H[:jd, :jd]), g[:jd]) @ Z[:jd])
+        if hist[-1] < tol:
+            info = 0
+            break
+    y = np.linalg.solve(np.triu(H[:jd, :jd]), g[:jd])
+    return x + y @ Z[:jd], info, np.array(hist)
+
+
+def solve_with_exact_schur_pc(n, xi, etan, etas, c, d, b_vec, u_vec, verbose=True):
+    """solve.py:210-238, the reference's small-n cross-check of the block preconditioner: the exact block-LU inverse
+    with dense pinv(F) / lstsq and an inner scipy gmres on the dense exact Schur complement S = -D F^-1 G
+    (preconditioner.py:343-346), first applied once to b (a direct solve), then used as M in fGMRES(maxiter=40).
+    Dense O(n^6) host algebra on matrices pulled from the GPU operators: n <= ExactSchurOperator.MAX_N.
+    Returns (u_direct, u_gmres, info, history)."""
+    from scipy.linalg import lstsq, pinv
+    from scipy.sparse.linalg import gmres as scipy_gmres
+    dx = dy = 1 / n
+    block_prec = MultiphaseBlockPreconditioner(n, xi, etan, etas)
+    A, S, F, D, G = block_prec.get_big_A_matrix(c=c, d_u=d)
+    Sd, Fd, Dd, Gd = S.toarray(), F.toarray(), D.toarray(), G.toarray()
+    A_inv = pinv(Fd)                                             # :217
+    nF = Fd.shape[1]
+
+    def exact_schur_op(v):                                       # :216-227
+        Ainv_v = lstsq(Fd, v[:nF])[0]
+        rhs_interim = np.matmul(Dd, Ainv_v) + v[nF:]
+        x_p = -1.0 * scipy_gmres(Sd, rhs_interim)[0]
+        G_xp = np.matmul(Gd, x_p)
+        Ainv_G_xp = np.matmul(A_inv, G_xp)
+        return np.concatenate((Ainv_v - Ainv_G_xp, x_p), axis=0)
+    b_vec = np.asarray(b_vec, dtype=np.float64)
+    u_direct = exact_schur_op(b_vec)                             # :229
+    if verbose:
+        print("\nPrinting error norms for solving Ax=b using schur complement:")
+        print_norms(u_direct, u_vec, dx, dy, n)
+        print("\nPrinting error norms for solving Ax=b using GMRES with exact Schur complement as preconditioner:")
+    cb = print_true_res_norm(A, b_vec, verbose=verbose) if verbose else None
+    u_gmres, info, hist = _fgmres_host_M(A, b_vec, exact_schur_op, 1e-8, 40, callback=cb)   # :237
+    if verbose:
+        print_norms(u_gmres, u_vec, dx, dy, n)
+    return u_direct, u_gmres, info, hist
 
 
 def solve_with_approx_schur_pc(n, xi, etan, etas, c, d, b_vec, u_vec, sub_solver: SubSolver | None = None,

@@ -86,3 +86,46 @@ def manufactured_device(plan, b_p_sign=-1.0):
     with torch.cuda.device(plan.device):
         check(plan.lib.mpbp_fill_manufactured(plan.h, u.data_ptr(), b.data_ptr(), float(b_p_sign), plan.stream()))
     return u, b
+
+
+def check_individual_operators(n, xi, L_n, D_n, XI_n, G_n, check_laplacian_op=True, check_divergence_op=True,
+                               check_xi_op=True, check_gradient_op=True, verbose=True):
+    """utils.check_individual_operators (utils.py:42-157): truncation error of each block operator applied to the
+    reference's analytic fields (thn = 1/4 sin 2 pi x sin 2 pi y + 1/2), printed the way the reference prints them.
+    The operators are the objects returned by `get_block_matrices` (they run on the GPU); the per-cell Python loops are
+    one vectorised evaluation.  Returns {"D": (L1, L2), "G": ..., "XI": ..., "L": ...} for the requested checks."""
+    from .preconditioner import thn, ths
+    h = 1 / n
+    r = np.arange(n, dtype=np.float64)[:, None] + np.zeros((1, n))
+    c = np.arange(n, dtype=np.float64)[None, :] + np.zeros((n, 1))
+    yu, xu, yv, xv, yp, xp = -(r + .5) * h, c * h, -r * h, (c + .5) * h, -(r + .5) * h, (c + .5) * h
+    ux = lambda y, x: np.sin(2 * PI * x) * np.cos(2 * PI * y)   # utils.py:53
+    uy = lambda y, x: np.cos(2 * PI * x) * np.sin(2 * PI * y)   # utils.py:54
+    u_n = np.concatenate([ux(yu, xu).ravel(), uy(yv, xv).ravel()])
+    p_n = ux(yp, xp).ravel()                                    # utils.py:55
+    w = h * h
+    out = {}
+
+    def report(name, exact, approx):
+        L2, L1 = weighted_L2(exact, approx, w), weighted_L1(exact, approx, w)
+        out[name] = (L1, L2)
+        if verbose:
+            print(f"Printing error norms for application of {name}:")
+            print(f"The L1_norm for n = {n} is {L1}")
+            print(f"The L2_norm for n = {n} is {L2}\n\n")
+    if check_divergence_op:
+        exact = (2 * PI * np.cos(2 * PI * xp) * np.cos(2 * PI * yp) + 1 / 2 * PI * np.sin(4 * PI * xp) * np.sin(4 * PI * yp)).ravel()  # :60
+        report("D", exact, D_n @ u_n)
+    if check_gradient_op:
+        gx = lambda y, x: PI / 2 * np.sin(2*PI*x) * np.sin(2*PI*y) * np.cos(2*PI*x) * np.cos(2*PI*y) + PI * np.cos(2*PI*x) * np.cos(2*PI*y)  # :85
+        gy = lambda y, x: -PI / 2 * np.sin(2*PI*x)**2 * np.sin(2*PI*y)**2 - PI * np.sin(2*PI*x) * np.sin(2*PI*y)                              # :86
+        report("G", np.concatenate([gx(yu, xu).ravel(), gy(yv, xv).ravel()]), G_n @ p_n)
+    if check_xi_op:
+        exact = np.concatenate([(xi * thn(yu, xu) * ths(yu, xu) * ux(yu, xu)).ravel(),
+                                (xi * thn(yv, xv) * ths(yv, xv) * uy(yv, xv)).ravel()])  # :122-123
+        report("XI", exact, XI_n @ u_n)
+    if check_laplacian_op:
+        lx = lambda y, x: -4*PI*PI*np.sin(2*PI*x)**2*np.sin(2*PI*y)*np.cos(2*PI*y) - 4*PI*PI*np.sin(2*PI*x)*np.cos(2*PI*y)  # :135
+        ly = lambda y, x: -4*PI*PI*np.sin(2*PI*x)*np.cos(2*PI*x)*np.sin(2*PI*y)**2 - 4*PI*PI*np.cos(2*PI*x)*np.sin(2*PI*y)  # :136
+        report("L", np.concatenate([lx(yu, xu).ravel(), ly(yv, xv).ravel()]), L_n @ u_n)
+    return out

@@ -557,6 +557,7 @@ def fgmres(A, b, M=None, x0=None, tol=1e-8, maxiter=150, callback=None, restart=
         V = np.zeros((m + 1, n))
         Z = np.zeros((m, n))
         Hm = np.zeros((m + 1, m))
+        Hraw = np.zeros((m + 1, m))  # the Hessenberg matrix before the Givens rotations (Ritz values)
         cs, sn = np.zeros(m), np.zeros(m)
         g = np.zeros(m + 1)
         g[0] = beta
@@ -571,6 +572,8 @@ def fgmres(A, b, M=None, x0=None, tol=1e-8, maxiter=150, callback=None, restart=
             Hm[j + 1, j] = np.linalg.norm(w)
             if Hm[j + 1, j] != 0:
                 V[j + 1] = w / Hm[j + 1, j]
+            Hraw[:, j] = Hm[:, j]
+            fgmres.last_hessenberg = Hraw[: j + 2, : j + 1]
             for i in range(j):
                 t = cs[i] * Hm[i, j] + sn[i] * Hm[i + 1, j]
                 Hm[i + 1, j] = -sn[i] * Hm[i, j] + cs[i] * Hm[i + 1, j]

@@ -232,6 +232,21 @@ def main():
                                                          refutils.weighted_L2(b_vec, bp_, w),
                                                          refutils.max_norm(b_vec, bp_)])
         print("kat", n, kat[f"opcheck_n{n}"])
+    # solve_with_exact_schur_pc (solve.py:210-238) run verbatim at n=8 (dense exact S; pyamg.fgmres -> oracle FGMRES)
+    n8, c8, d8, xi8, en8, es8 = 8, 1, -1, 1.0, 100.0, 1.0
+    A8, b8, u8 = refsolve.main(n=n8, c=c8, d=d8, xi=xi8, eta_n=en8, eta_s=es8)
+    _state.clear()
+    with contextlib.redirect_stdout(io.StringIO()) as buf:
+        refsolve.solve_with_exact_schur_pc(n8, xi8, en8, es8, c8, d8, b8, u8)
+    vals = [float(v) for v in re.findall(r"_norm for n = \d+ is ([0-9.eE+-]+)", buf.getvalue())]
+    kat["exact_schur_n8_norms"] = np.array(vals)          # direct solve (L1, L2, max), then fGMRES (L1, L2, max)
+    kat["exact_schur_n8_hist"] = _state["hist"]
+    kat["exact_schur_n8_S_fro"] = np.array(np.linalg.norm(refpc.MultiphaseBlockPreconditioner(n8, xi8, en8, es8).get_big_A_matrix(c=c8, d_u=d8)[1]))
+    print("exact schur n=8:", vals, "its", len(_state["hist"]))
+    # get_thn_vals (preconditioner.py:26-84) for every u-face of an 8 x 8 grid, both phases
+    bp8 = refpc.MultiphaseBlockPreconditioner(8, 1.0, 1.0, 1.0)
+    kat["thn_vals_n8"] = np.array([[[bp8.get_thn_vals(8, r, cc, bool(ph)) for cc in range(8)] for r in range(8)]
+                                   for ph in (0, 1)])
     np.savez_compressed(os.path.join(HERE, "known_answers.npz"), **kat)
 
 

@@ -107,3 +107,18 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "mpbp_oracle" not in src and "oracle/" not in src, f
+
+
+def test_get_thn_vals_matches_reference_table():
+    """MultiphaseBlockPreconditioner.get_thn_vals (preconditioner.py:26-84): the six volume fractions around every
+    u-face of an 8 x 8 grid, both phases, vs the table produced by the reference's own method (host-only code)."""
+    import numpy as np
+    import mp_block_preconditioners_b200 as mp
+    from conftest import golden
+    kat = golden("known_answers.npz")
+    if "thn_vals_n8" not in kat.files:
+        import pytest
+        pytest.skip("fixture predates get_thn_vals")
+    bp = mp.MultiphaseBlockPreconditioner(8, 1.0, 1.0, 1.0)
+    got = np.array([[[bp.get_thn_vals(8, r, c, bool(ph)) for c in range(8)] for r in range(8)] for ph in (0, 1)])
+    assert np.abs(got - kat["thn_vals_n8"]).max() < 1e-15

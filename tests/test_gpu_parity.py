@@ -228,35 +228,40 @@ def test_unpreconditioned_matches_oracle(mp):
 
 
 def test_known_answer_operator_checks(mp):
-    """utils.check_individual_operators (utils.py:42-157) re-run on the GPU blocks: L1/L2 truncation
-    errors of D, G, XI, L for n = 8, 16, 32 vs the values printed by the reference."""
+    """utils.check_individual_operators (utils.py:42-157) on the GPU blocks of get_block_matrices: L1/L2 truncation
+    errors of D, G, XI, L for n = 8, 16, 32 vs the values printed by the reference (second order)."""
     kat = golden("known_answers.npz")
-    PI = np.pi
     for n in (8, 16, 32):
-        h = 1 / n
         bp = mp.MultiphaseBlockPreconditioner(n, 1.0, 1.0, 1.0)
         L, D, XI, G = bp.get_block_matrices(is_ths=False)
-        r = np.arange(n)[:, None] + np.zeros((1, n))
-        c = np.arange(n)[None, :] + np.zeros((n, 1))
-        yu, xu, yv, xv, yp, xp = -(r + .5) * h, c * h, -r * h, (c + .5) * h, -(r + .5) * h, (c + .5) * h
-        ux = lambda y, x: np.sin(2 * PI * x) * np.cos(2 * PI * y)
-        uy = lambda y, x: np.cos(2 * PI * x) * np.sin(2 * PI * y)
-        u = np.concatenate([ux(yu, xu).ravel(), uy(yv, xv).ravel()])
-        pvec = ux(yp, xp).ravel()
-        thn, ths = mp.thn, mp.ths
-        w = h * h
-        exact_D = (2 * PI * np.cos(2 * PI * xp) * np.cos(2 * PI * yp) + 0.5 * PI * np.sin(4 * PI * xp) * np.sin(4 * PI * yp)).ravel()
-        gx = lambda y, x: PI / 2 * np.sin(2*PI*x) * np.sin(2*PI*y) * np.cos(2*PI*x) * np.cos(2*PI*y) + PI * np.cos(2*PI*x) * np.cos(2*PI*y)
-        gy = lambda y, x: -PI / 2 * np.sin(2*PI*x)**2 * np.sin(2*PI*y)**2 - PI * np.sin(2*PI*x) * np.sin(2*PI*y)
-        exact_G = np.concatenate([gx(yu, xu).ravel(), gy(yv, xv).ravel()])
-        exact_XI = np.concatenate([(thn(yu, xu) * ths(yu, xu) * ux(yu, xu)).ravel(), (thn(yv, xv) * ths(yv, xv) * uy(yv, xv)).ravel()])
-        lx = lambda y, x: -4*PI*PI*np.sin(2*PI*x)**2*np.sin(2*PI*y)*np.cos(2*PI*y) - 4*PI*PI*np.sin(2*PI*x)*np.cos(2*PI*y)
-        ly = lambda y, x: -4*PI*PI*np.sin(2*PI*x)*np.cos(2*PI*x)*np.sin(2*PI*y)**2 - 4*PI*PI*np.cos(2*PI*x)*np.sin(2*PI*y)
-        exact_L = np.concatenate([lx(yu, xu).ravel(), ly(yv, xv).ravel()])
-        got = []
-        for ex, ap in ((exact_D, D @ u), (exact_G, G @ pvec), (exact_XI, XI @ u), (exact_L, L @ u)):
-            got += [mp.weighted_L1(ex, ap, w), mp.weighted_L2(ex, ap, w)]
+        res = mp.check_individual_operators(n, 1.0, L, D, XI, G, True, True, True, True, verbose=False)
+        got = [v for k in ("D", "G", "XI", "L") for v in res[k]]
         assert np.allclose(got, kat[f"opcheck_n{n}"], rtol=1e-7), (n, got, kat[f"opcheck_n{n}"])
+
+
+def test_exact_schur_small_n_path(mp):
+    """solve_with_exact_schur_pc (solve.py:210-238) with the dense S = -D F^-1 G built from the GPU
+    operators (preconditioner.py:343-346), vs the reference's own run at n=8: ||S||_F, the error norms of the direct
+    block-LU solve and of the fGMRES(maxiter=40) solve, and the residual history."""
+    kat = golden("known_answers.npz")
+    if "exact_schur_n8_norms" not in kat.files:
+        pytest.skip("fixture predates the exact-Schur path")
+    n, c, d, xi, eta_n, eta_s = 8, 1, -1, 1.0, 100.0, 1.0
+    A, b_vec, u_vec = mp.main(n=n, c=c, d=d, xi=xi, eta_n=eta_n, eta_s=eta_s)
+    S = mp.MultiphaseBlockPreconditioner(n, xi, eta_n, eta_s).get_big_A_matrix(c=c, d_u=d)[1]
+    assert S.shape == (n * n, n * n)
+    assert abs(np.linalg.norm(S.toarray()) - float(kat["exact_schur_n8_S_fro"])) < 1e-9 * float(kat["exact_schur_n8_S_fro"])
+    u_direct, u_gmres, info, hist = mp.solve_with_exact_schur_pc(n, xi, eta_n, eta_s, c, d, b_vec, u_vec, verbose=False)
+    w = (1 / n) ** 2
+    got = [mp.weighted_L1(u_direct, u_vec, w), mp.weighted_L2(u_direct, u_vec, w), mp.max_norm(u_direct, u_vec),
+           mp.weighted_L1(u_gmres, u_vec, w), mp.weighted_L2(u_gmres, u_vec, w), mp.max_norm(u_gmres, u_vec)]
+    assert np.allclose(got, kat["exact_schur_n8_norms"], rtol=1e-4), (got, kat["exact_schur_n8_norms"])
+    ref = kat["exact_schur_n8_hist"]
+    assert abs(len(hist) - len(ref)) <= 1
+    k = min(len(hist), len(ref), 4)
+    assert np.allclose(hist[:k], ref[:k], rtol=1e-3)
+    with pytest.raises(NotImplementedError):
+        mp.MultiphaseBlockPreconditioner(64, 1.0, 1.0, 1.0).get_big_A_matrix(1.0, -1.0)[1].toarray()
 
 
 def test_apply_check_known_answers(mp):
@@ -472,3 +477,66 @@ def test_full_size_properties(mp, n):
         Mx, My = M @ x2, M @ y2
         lin = M @ (x2 + 0.5 * y2)
         assert float(torch.linalg.norm(lin - (Mx + 0.5 * My))) < 1e-9 * float(torch.linalg.norm(Mx))
+
+
+def test_spectral_diagnostics_from_the_hessenberg(mp):
+    """Ritz values of A M^-1 from the GMRES Hessenberg replace the reference's dense
+    compute_preconditioned_A + SLEPc analysis (solve.py:103-200, :304-309).  (i) the GPU's Hessenberg matrix equals the
+    oracle's FGMRES Hessenberg on a well-conditioned configuration (Jacobi sub-solves), 1e-8 relative; (ii) at n=8 the
+    Ritz values lie in the convex hull of the dense spectrum of A M^-1 and the largest one has converged to its
+    largest eigenvalue (what SLEPc's default largest-magnitude EPS would return, solve.py:121-123)."""
+    g = golden("solve_jacobi_n16_eta100.npz")
+    n, xi, eta_n, eta_s, c, d = g["params"]
+    n = int(n)
+    subkw = dict(kind="jacobi", F_sweeps=20, P_sweeps=20, omega=0.8)
+    bp = mp.MultiphaseBlockPreconditioner(n, xi, eta_n, eta_s, sub_solver=mp.SubSolver(**subkw))
+    A = bp.get_big_A_matrix(c=c, d_u=d)[0]
+    M = bp.approx_schur_operator(c=c, d_u=d)
+    mp.fgmres(A, g["b_vec"], M=M, tol=1e-8, maxiter=150)
+    H = mp.last_hessenberg(A)
+    ops = O.Operators(n, xi, eta_n, eta_s, c, d)
+    Mo = O.ApproxSchur(ops, O.SubSolverConfig(kind="jacobi", sweeps=20, omega=0.8))
+    O.fgmres(ops.A, g["b_vec"], M=Mo.linear_operator(), tol=1e-8, maxiter=150)
+    Ho = O.fgmres.last_hessenberg
+    assert H.shape == Ho.shape == (len(g["hist"]) + 1, len(g["hist"]))
+    assert np.abs(H - Ho).max() < 1e-8 * np.abs(Ho).max()
+    sd = mp.spectral_diagnostics(A)
+    ritz_o = np.linalg.eigvals(Ho[:-1])
+    assert np.abs(np.sort_complex(sd["ritz"]) - np.sort_complex(ritz_o)).max() < 1e-6 * np.abs(ritz_o).max()
+    # small dense check of what the Ritz values mean
+    n = 8
+    bp = mp.MultiphaseBlockPreconditioner(n, 1.0, 100.0, 1.0, sub_solver=mp.SubSolver(kind="mg", F_cycles=4, P_cycles=4, cheb=True))
+    A = bp.get_big_A_matrix(1.0, -1.0)[0]
+    M = bp.approx_schur_operator(1.0, -1.0)
+    Ad = A.toarray()
+    Md = np.column_stack([M @ e for e in np.eye(5 * n * n)])
+    ev = np.linalg.eigvals(Ad @ Md)
+    rng = np.random.default_rng(3)
+    mp.fgmres(A, rng.standard_normal(5 * n * n), M=M, tol=1e-14, maxiter=60)
+    sd = mp.spectral_diagnostics(A)
+    assert sd["k"] >= 20
+    assert sd["ritz"].real.max() <= ev.real.max() * (1 + 1e-6) and sd["ritz"].real.min() >= ev.real.min() - 1e-6 * abs(ev).max()
+    assert abs(abs(sd["largest"][0]) - abs(ev).max()) < 1e-3 * abs(ev).max()
+
+
+def test_iterate_callback_is_one_pass_per_iteration(mp):
+    """fgmres(callback=) hands out x_k = x0 + Z y_k each inner iteration (pyamg semantics, solve.py:285, :163-169): the
+    last iterate is the returned solution, every iterate's true residual tracks the recurrence residual, and the
+    whole callback run launches only a few kernels more than the plain solve (no re-solves)."""
+    g = golden("solve_mgcheb_n32_eta1.npz")
+    n, xi, eta_n, eta_s, c, d = g["params"]
+    bp = mp.MultiphaseBlockPreconditioner(int(n), xi, eta_n, eta_s, sub_solver=mp.SubSolver(kind="mg", F_cycles=4, P_cycles=4, cheb=True))
+    A = bp.get_big_A_matrix(c=c, d_u=d)[0]
+    M = bp.approx_schur_operator(c=c, d_u=d)
+    l0 = A.plan.launches
+    x_plain, _ = mp.fgmres(A, g["b_vec"], M=M, tol=1e-8, maxiter=150)
+    l1 = A.plan.launches
+    its = []
+    x_cb, _ = mp.fgmres(A, g["b_vec"], M=M, tol=1e-8, maxiter=150, callback=lambda xk: its.append(xk.copy()))
+    l2 = A.plan.launches
+    assert len(its) == len(mp.fgmres.last_history)
+    assert np.array_equal(x_cb, x_plain) and relerr(its[-1], x_plain) < 1e-12
+    bn = np.linalg.norm(g["b_vec"])
+    true = np.array([np.linalg.norm(g["b_vec"] - A @ xk) / bn for xk in its])
+    assert np.allclose(true, mp.fgmres.last_history, rtol=1e-3)
+    assert (l2 - l1) - (l1 - l0) <= 4 * len(its)
