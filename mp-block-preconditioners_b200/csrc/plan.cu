@@ -60,6 +60,7 @@ struct Level {
   int n = 0, rows = 0, row0 = 0;
   bool dist = false;  // slab-distributed over ranks (needs halo exchange); false = whole grid on this rank
   Geo geo{};   // strip geometry for the register-heavy k_stokes kernels (~5 blocks/SM)
+  Geo geo4{};  // ... for the 128-register variants (prolongation fused into the sweep: 4 blocks/SM)
   Geo geoL{};  // strip geometry for the light kernels (k_poisson, k_div, k_grad, k_jacobi0_F: 12-16 blocks/SM)
   Phys ph{};
   double* th = nullptr;    // padded theta: (rows+2) x n
@@ -251,8 +252,7 @@ static void carve(mpbp_plan* p, Bump& B) {
 // launch helpers
 // ---------------------------------------------------------------------------------------------
 static inline dim3 stencil_grid(const Level& v, const Geo& g) {
-  return dim3((unsigned)((v.n + kWarpCols * kBlockWarps - 1) / (kWarpCols * kBlockWarps)),
-              (unsigned)((v.rows + g.rs - 1) / g.rs));
+  return dim3((unsigned)((v.n + kWarpCols * kBlockWarps - 1) / (kWarpCols * kBlockWarps)), (unsigned)strip_count(g));
 }
 // Rows per strip: long strips amortise the two re-read halo rows, but the block count should fill whole
 // waves of `cap` resident blocks (wave quantisation costs up to 2x on the slab sizes of 4-8 GPUs).
@@ -272,6 +272,26 @@ static int choose_rs(int gx, int rows, int cap) {
     if (score > best + 1e-12) best = score, best_rs = rs;
   }
   return best_rs;
+}
+// Strip decomposition of a level for kernels with `cap` resident blocks on the device.  Large levels: SINGLE WAVE --
+// as many interior strips as fit next to each other (gx * S <= cap), so the launch has no tail wave, plus two short
+// edge strips that are scheduled first (halo waits / pushes, general code path).  Small levels keep the wave-aware
+// uniform strips of choose_rs.
+static void set_strips(Geo& g, int gx, int rows, int cap) {
+  g.re = 0;
+  const int e = 8;
+  const int S = cap / std::max(gx, 1);
+  if (!(rows & 1) && rows >= 64 && S >= 1) {
+    int rs = ((rows - 2 * e) + S - 1) / S;
+    rs += rs & 1;
+    if (rs >= 16) {
+      g.rs = rs;
+      g.re = e;
+      return;
+    }
+  }
+  g.rs = choose_rs(gx, rows, cap);
+  if (!(rows & 1) && (g.rs & 1)) g.rs += 1;
 }
 static inline int ew_blocks(size_t len) { return (int)std::min<size_t>((len + 255) / 256, 148 * 16); }
 
@@ -374,12 +394,12 @@ static void sx_launch(mpbp_plan* p, dim3 grid, const StokesArgs& a) {
 static int launch_sx(mpbp_plan* p, int l, SxKind k, StokesArgs& a) {
   Level& v = p->lev[l];
   a.th = v.th;
-  a.g = v.geo;
+  a.g = (k.in == 2) ? v.geo4 : v.geo;
   a.ph = v.ph;
   const int wc = (k.ep == 2) ? WarpTile<2>::cols : WarpTile<0>::cols;
-  if ((k.in == 2 || k.ep == 2) && ((v.rows & 1) || (v.geo.rs & 1) || (v.dist && k.ep == 2)))
-    return set_err(MPBP_E_STATE, "internal: row-pair kernel on an odd / distributed level (rows %d, rs %d)", v.rows, v.geo.rs);
-  const dim3 grid((unsigned)((v.n + wc * kBlockWarps - 1) / (wc * kBlockWarps)), (unsigned)((v.rows + v.geo.rs - 1) / v.geo.rs));
+  if ((k.in == 2 || k.ep == 2) && ((v.rows & 1) || (a.g.rs & 1) || (a.g.re & 1) || (v.dist && k.ep == 2)))
+    return set_err(MPBP_E_STATE, "internal: row-pair kernel on an odd / distributed level (rows %d, rs %d)", v.rows, a.g.rs);
+  const dim3 grid((unsigned)((v.n + wc * kBlockWarps - 1) / (wc * kBlockWarps)), (unsigned)strip_count(a.g));
   if (k.push) a.po = push_out(p);
   const int key = k.in * 10000 + k.mode * 1000 + (k.with_p ? 100 : 0) + k.ep * 10 + (k.push ? 1 : 0);
   switch (key) {
@@ -843,7 +863,7 @@ static int vcycle(mpbp_plan* p, int l, bool isF, const double* b, double* x, con
   }
   double* t = isF ? v.tF : v.tP;
   double* r = isF ? v.rF : v.rP;
-  const bool even = !(v.rows & 1) && !(v.geo.rs & 1);
+  const bool even = !(v.rows & 1) && !(v.geo.rs & 1) && !(v.geo4.rs & 1);
   const bool dist_ok = !v.dist || (p->p2p && p->push_fused);  // distributed levels: fused variants need the peer-memory halos
   const bool fuse_pre = isF && (p->fuse & 1) && dist_ok && c.nu1 == 2 && v.wdF != nullptr;
   const bool fuse_rr = isF && (p->fuse & 4) && !v.dist && even;                  // residual + restriction
@@ -1342,18 +1362,34 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
       int sms_ = 148, dev_ = 0;
       cudaGetDevice(&dev_);
       cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, dev_);
-      v.geo.rs = choose_rs(gx, v.rows, 5 * sms_);
       v.geo.pf = 3;  // measured best on B200 at 4096^2 (profiles/r1_tuning.txt)
       if (const char* e = getenv("MPBP_PF")) v.geo.pf = std::max(0, std::min(atoi(e), 64));
-      if (const char* e = getenv("MPBP_RS")) v.geo.rs = std::max(1, std::min(atoi(e), v.rows));
-      if (!(v.rows & 1) && (v.geo.rs & 1)) v.geo.rs += 1;
+      v.geo4 = v.geo;
       v.geoL = v.geo;
-      {  // light kernels (16 resident blocks/SM): 32-row strips, halved until the grid has >= 4 blocks per SM
+      const bool wave = !(getenv("MPBP_WAVE") && atoi(getenv("MPBP_WAVE")) == 0);
+      if (wave) {
+        set_strips(v.geo, gx, v.rows, 5 * sms_);
+        set_strips(v.geo4, gx, v.rows, 4 * sms_);
+      } else {
+        v.geo.rs = v.geo4.rs = choose_rs(gx, v.rows, 5 * sms_);
+        if (!(v.rows & 1) && (v.geo.rs & 1)) v.geo.rs = (v.geo4.rs += 1);
+      }
+      if (const char* e = getenv("MPBP_RS")) {
+        v.geo.rs = v.geo4.rs = std::max(1, std::min(atoi(e), v.rows));
+        if (!(v.rows & 1) && (v.geo.rs & 1)) v.geo.rs = (v.geo4.rs += 1);
+        v.geo.re = v.geo4.re = 0;
+      }
+      {  // light kernels (16 resident blocks/SM)
         int rs = 32;
         while (rs > 4 && gx * ((v.rows + rs - 1) / rs) < 4 * sms_) rs /= 2;
         v.geoL.rs = std::max(1, std::min(rs, v.rows));
+        v.geoL.re = 0;
+        if (wave && gx * ((v.rows + 31) / 32) >= 16 * sms_) set_strips(v.geoL, gx, v.rows, 16 * sms_);
       }
-      if (const char* e = getenv("MPBP_RSL")) v.geoL.rs = std::max(1, std::min(atoi(e), v.rows));
+      if (const char* e = getenv("MPBP_RSL")) {
+        v.geoL.rs = std::max(1, std::min(atoi(e), v.rows));
+        v.geoL.re = 0;
+      }
     }
   }
   int dev = 0, sms = 148;
@@ -1641,7 +1677,7 @@ static double vcycle_bytes(const mpbp_plan* p, int l, bool isF, bool with_ep) {
   const double N = (double)p->lev[l].fs();
   if (l == L - 1) return 0.0;  // dense coarse solve: negligible
   const Level& v = p->lev[l];
-  const bool even = !(v.rows & 1) && !(v.geo.rs & 1);
+  const bool even = !(v.rows & 1) && !(v.geo.rs & 1) && !(v.geo4.rs & 1);
   double by = 0.0;
   // the epilogue replaces the write of z (4N or N doubles) by read d, x + write d, x (upper bound: middle cycles)
   const double ep_extra = with_ep ? (isF ? 4 : 1) * 8.0 * N * 3.0 : 0.0;

@@ -184,9 +184,16 @@ struct Geo {
   int n;     // columns (= global grid size of the level)
   int rows;  // local rows of the slab
   int row0;  // global index of local row 0
-  int rs;    // rows per strip (gridDim.y strips)
+  int rs;    // rows per strip
   int pf;    // L2 prefetch distance in rows (0 = off)
+  int re;    // > 0: the first and last strip are `re` rows short strips and the rows in between are cut into strips of
+             // `rs` rows (single-wave decomposition, see strip_rows); 0: uniform strips of `rs` rows
 };
+// number of strips (= gridDim.y) of a geometry
+__host__ __device__ __forceinline__ int strip_count(const Geo& g) {
+  if (g.re > 0) return 2 + (g.rows - 2 * g.re + g.rs - 1) / g.rs;
+  return (g.rows + g.rs - 1) / g.rs;
+}
 
 // Software prefetch into L2 of the row `pf` rows ahead: three lanes (0, 16, 31) cover the <= 3 cache
 // lines a warp's 32 columns touch.  Costs no registers, turns the later LDG into an L2 hit.
@@ -314,6 +321,23 @@ __device__ __forceinline__ int strip_of_block() {
   const int S = (int)gridDim.y, sy = (int)blockIdx.y;
   return (S > 2) ? (sy == 0 ? 0 : (sy == 1 ? S - 1 : sy - 1)) : sy;
 }
+// Rows [r0, r1) of this block's strip.  Large levels use the SINGLE-WAVE decomposition: the number of interior strips
+// is chosen so that all blocks of the launch are resident at once (no tail wave: with uniform 32-row strips a
+// 4096^2 sweep was 6.05 waves of 5 blocks/SM and paid for 7), and two SHORT edge strips, scheduled first, carry the
+// halo waits / pushes and the general (periodic / halo) code path, so their slots are recycled almost immediately.
+__device__ __forceinline__ bool strip_rows(const Geo& g, int& r0, int& r1) {
+  const int s = strip_of_block();
+  if (g.re > 0) {
+    const int S = (int)gridDim.y;
+    if (s == 0) { r0 = 0; r1 = g.re; }
+    else if (s == S - 1) { r0 = g.rows - g.re; r1 = g.rows; }
+    else { r0 = g.re + (s - 1) * g.rs; r1 = min(r0 + g.rs, g.rows - g.re); }
+  } else {
+    r0 = s * g.rs;
+    r1 = min(r0 + g.rs, g.rows);
+  }
+  return r0 < r1;
+}
 
 // (the velocity-block / full-system marching kernel with its fused variants lives in stokes.cuh)
 
@@ -329,9 +353,8 @@ __global__ void __launch_bounds__(kBlockThreads) k_jacobi0_F(const double* __res
   const LaneGeom lg = lane_geom(g.n);
   if (!lg.alive) return;
   const int n = g.n, rows = g.rows, c = lg.cc;
-  const int r0 = blockIdx.y * g.rs;
-  const int r1 = min(r0 + g.rs, rows);
-  if (r0 >= rows) return;
+  int r0, r1;
+  if (!strip_rows(g, r0, r1)) return;
   double sxf = 0.0, sxc = 0.0;
   if (ph.mass_mode) {
     sxf = ph.sxf[c];
@@ -401,9 +424,8 @@ __global__ void __launch_bounds__(kBlockThreads) k_poisson(VecIn pin, const doub
   const LaneGeom lg = lane_geom(g.n);
   if (!lg.alive) return;
   const int n = g.n, rows = g.rows, c = lg.cc;
-  const int r0 = strip_of_block() * g.rs;
-  const int r1 = min(r0 + g.rs, rows);
-  if (r0 >= rows) return;
+  int r0, r1;
+  if (!strip_rows(g, r0, r1)) return;
   if (MODE != 3) halo_wait(pin, r0 == 0, r1 == rows);
   PushCtx pc{};
   if (PUSH) pc = push_begin(po, r0 == 0, r1 == rows);
@@ -464,9 +486,8 @@ __global__ void __launch_bounds__(kBlockThreads) k_div(VecIn win, const double* 
   const LaneGeom lg = lane_geom(g.n);
   if (!lg.alive) return;
   const int n = g.n, rows = g.rows, c = lg.cc;
-  const int r0 = strip_of_block() * g.rs;
-  const int r1 = min(r0 + g.rs, rows);
-  if (r0 >= rows) return;
+  int r0, r1;
+  if (!strip_rows(g, r0, r1)) return;
   halo_wait(win, r0 == 0, r1 == rows);
   double th_m = th_row(th, r0 - 1, n)[c];
   double th_c = th_row(th, r0, n)[c];
@@ -498,9 +519,8 @@ __global__ void __launch_bounds__(kBlockThreads) k_grad(VecIn pin, const double*
   const LaneGeom lg = lane_geom(g.n);
   if (!lg.alive) return;
   const int n = g.n, rows = g.rows, c = lg.cc;
-  const int r0 = strip_of_block() * g.rs;
-  const int r1 = min(r0 + g.rs, rows);
-  if (r0 >= rows) return;
+  int r0, r1;
+  if (!strip_rows(g, r0, r1)) return;
   halo_wait(pin, r0 == 0, r1 == rows);
   PushCtx pc{};
   if (PUSH) pc = push_begin(po, r0 == 0, r1 == rows);

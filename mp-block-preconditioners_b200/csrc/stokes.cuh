@@ -402,9 +402,8 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) k_stokes_x(const __grid_c
   const int rows = a.g.rows;
   // strip order: first strip, LAST strip, then the interior -- both edge strips (the ones that wait for the ring
   // neighbours' rows and push this rank's own) run in the first wave and their transfers overlap the interior
-  const int r0 = strip_of_block() * a.g.rs;
-  if (r0 >= rows) return;
-  const int r1 = min(r0 + a.g.rs, rows);
+  int r0, r1;
+  if (!strip_rows(a.g, r0, r1)) return;
   // interior strips touch rows r0-2 .. r1+1 (and the coarse rows under them) only: all inside the slab
   if (r0 >= 2 && r1 + 4 <= rows) stokes_march<IN, MODE, WITH_P, EP, PUSH, false>(a, r0, r1);
   else stokes_march<IN, MODE, WITH_P, EP, PUSH, true>(a, r0, r1);

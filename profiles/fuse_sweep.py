@@ -31,10 +31,10 @@ def timeit(fn, reps=5):
     return e0.elapsed_time(e1) / reps
 
 
-for env in [dict(MPBP_FUSE="1"), dict(MPBP_FUSE="3"), dict(MPBP_FUSE="5"), dict(MPBP_FUSE="7"),
-            dict(MPBP_FUSE="7", MPBP_GRAPH="0"), dict(MPBP_FUSE="7", MPBP_COARSE="64"),
-            dict(MPBP_FUSE="7", MPBP_COARSE="128"), dict(MPBP_FUSE="7", MPBP_PF="2"), dict(MPBP_FUSE="7", MPBP_PF="4")]:
-    for k in ("MPBP_FUSE", "MPBP_GRAPH", "MPBP_COARSE", "MPBP_PF"):
+KNOBS = ("MPBP_FUSE", "MPBP_GRAPH", "MPBP_COARSE", "MPBP_PF", "MPBP_WAVE")
+for env in [dict(), dict(MPBP_WAVE="0"), dict(MPBP_FUSE="1"), dict(MPBP_FUSE="3"), dict(MPBP_FUSE="5"),
+            dict(MPBP_GRAPH="0"), dict(MPBP_COARSE="64"), dict(MPBP_PF="2"), dict(MPBP_PF="4"), dict(MPBP_PF="6")]:
+    for k in KNOBS:
         os.environ.pop(k, None)
     os.environ.update(env)
     bp = mp.MultiphaseBlockPreconditioner(n, w["xi"], w["eta_n"], w["eta_s"], sub_solver=mp.SubSolver(**bench.SUB))
@@ -45,11 +45,14 @@ for env in [dict(MPBP_FUSE="1"), dict(MPBP_FUSE="3"), dict(MPBP_FUSE="5"), dict(
     x4 = torch.zeros(4 * N, dtype=torch.float64, device="cuda")
     y5 = torch.empty(5 * N, dtype=torch.float64, device="cuda")
     st = p.stream()
+    ms_j = timeit(lambda: check(lib.mpbp_jacobi_F(p.h, b.data_ptr(), x4.data_ptr(), 10, 0.8, st))) / 10
+    ms_a = timeit(lambda: check(lib.mpbp_apply_A(p.h, b.data_ptr(), y5.data_ptr(), st)), reps=10)
     ms_v = timeit(lambda: check(lib.mpbp_vcycle_F(p.h, b.data_ptr(), x4.data_ptr(), st)))
     ms_s = timeit(lambda: check(lib.mpbp_solve_F(p.h, b.data_ptr(), x4.data_ptr(), st)))
     ms_p = timeit(lambda: check(lib.mpbp_precond_apply(p.h, b.data_ptr(), y5.data_ptr(), st)))
     by = p.precond_bytes()
-    rec = dict(env=env, vcycle_F_ms=ms_v, solve_F_ms=ms_s, precond_ms=ms_p, precond_GB=by / 1e9, gbs=by / ms_p / 1e6,
+    rec = dict(env=env, jacobi_F_ms=ms_j, jacobi_frac=104 * N / ms_j / 1e6 / peak, apply_A_ms=ms_a,
+               apply_A_frac=88 * N / ms_a / 1e6 / peak, vcycle_F_ms=ms_v, solve_F_ms=ms_s, precond_ms=ms_p, precond_GB=by / 1e9, gbs=by / ms_p / 1e6,
                frac=by / ms_p / 1e6 / peak)
     out.append(rec)
     print(rec, flush=True)

@@ -4,6 +4,8 @@
 set -x
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q -s 2>&1 | grep -E "passed|failed|FAILED|\[large|\[hist|Error" | cut -c1-700 | tail -70
+timeout 600 python profiles/fuse_sweep.py 4096 2>&1 | tail -12
+timeout 600 python profiles/kernel_table.py 4096 > gpurun_out/r2_kernel_table_b.txt 2>&1; cat gpurun_out/r2_kernel_table_b.txt
 export MPBP_GRAPH=0
 SEC="--section SpeedOfLight --section MemoryWorkloadAnalysis --section Occupancy --section WarpStateStats --section LaunchStats --section SchedulerStats --section ComputeWorkloadAnalysis"
 timeout 300 python profiles/prof_kernels.py > gpurun_out/prof_plain.log 2>&1 && \

@@ -68,7 +68,7 @@ def stokes_fused(variant, n, prm, mass_mode, theta, x, b, wd=None, ec=None, rs=8
 
 
 def stokes_x(IN, MODE, EP, n, prm, mass_mode, theta, x, b=None, with_p=False, wd=None, ec=None, d=None, xk=None,
-             cheb=None, flags=(1, 1, 1), rs=8, pf=3, omega=0.8):
+             cheb=None, flags=(1, 1, 1), rs=8, pf=3, omega=0.8, re=0):
     """csrc/stokes.cuh: k_stokes_x<IN, MODE, WITH_P, EP>.  Returns y (EP 0), (d, xk) (EP 1) or the coarse rhs (EP 2)."""
     c = lambda v: None if v is None else np.ascontiguousarray(v, dtype=np.float64)
     x, b, wd, ec = c(x), c(b), c(wd), c(ec)
@@ -79,7 +79,7 @@ def stokes_x(IN, MODE, EP, n, prm, mass_mode, theta, x, b=None, with_p=False, wd
     ch = None if cheb is None else np.array(cheb, dtype=np.float64)
     fl = (C.c_int * 3)(*flags)
     load().emu_stokes_x(IN, MODE, int(with_p), EP, n, _p(prm), mass_mode, _p(thp), _p(x), _p(b), _p(wd), _p(ec),
-                        _p(d), _p(xk), _p(ch), fl, _p(out), rs, pf, C.c_double(omega))
+                        _p(d), _p(xk), _p(ch), fl, _p(out), rs, pf, C.c_double(omega), re)
     return (d, xk) if EP == 1 else out
 
 

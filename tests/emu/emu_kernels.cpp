@@ -82,11 +82,11 @@ void emu_stokes_fused(int variant, int n, const double* prm, int mass_mode, cons
 // (EP 1: d / xk are updated in place), or the coarse rhs (EP 2)
 void emu_stokes_x(int in, int mode, int with_p, int ep, int n, const double* prm, int mass_mode, const double* th_pad,
                   const double* x, const double* b, const double* wd, const double* ec, double* d, double* xk,
-                  const double* cheb, const int* flags, double* out, int rs, int pf, double omega) {
+                  const double* cheb, const int* flags, double* out, int rs, int pf, double omega, int re) {
   Tables t;
   StokesArgs a{};
   a.ph = make_phys(n, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], prm[6], mass_mode, t);
-  a.g = Geo{n, n, 0, rs, pf};
+  a.g = Geo{n, n, 0, rs, pf, re};
   a.xin = whole_grid_view(x, n);
   a.th = th_pad;
   a.b = b;
@@ -99,7 +99,7 @@ void emu_stokes_x(int in, int mode, int with_p, int ep, int n, const double* prm
   if (cheb) a.ce = ChebEp{cheb[0], cheb[1], d, xk, flags[0], flags[1], flags[2]};
   a.bc = out;
   const int wc = (ep == 2) ? WarpTile<2>::cols : WarpTile<0>::cols;
-  const dim3 grid((n + wc * kBlockWarps - 1) / (wc * kBlockWarps), (n + rs - 1) / rs);
+  const dim3 grid((n + wc * kBlockWarps - 1) / (wc * kBlockWarps), strip_count(a.g));
   const int key = in * 1000 + mode * 100 + with_p * 10 + ep;
   emu::launch(grid, dim3(kBlockThreads), [&] {
     switch (key) {

@@ -135,11 +135,13 @@ def test_fused_halo_push_chain_on_the_shim(P, rs):
     assert relerr(got, b - ops.F @ x2) < 1e-12
 
 
-@pytest.mark.parametrize("n,analytic,rs", [(8, True, 4), (12, False, 6), (32, True, 4), (36, False, 8)])
-def test_unified_marching_kernel_and_its_fused_variants(n, analytic, rs):
+@pytest.mark.parametrize("n,analytic,rs,re", [(8, True, 4, 0), (12, False, 6, 0), (32, True, 4, 0), (36, False, 8, 0),
+                                              (32, True, 6, 4), (36, False, 10, 8)])
+def test_unified_marching_kernel_and_its_fused_variants(n, analytic, rs, re):
     """csrc/stokes.cuh: every (IN, MODE, EP) instantiation the plan launches, against compositions of the oracle's
     operators.  n=32/36 with short strips exercise the lean interior instantiation (strips with r0 >= 2 and
-    r1 + 4 <= rows) next to the edge one; n=36 is not a multiple of the warp tile."""
+    r1 + 4 <= rows) next to the edge one; n=36 is not a multiple of the warp tile; re > 0 is the single-wave
+    decomposition (two short edge strips of `re` rows, interior strips of `rs` rows, the last one ragged)."""
     theta, ops, prm = _setup(n, analytic)
     mm = 1 if analytic else 0
     rng = np.random.default_rng(n + rs)
@@ -148,7 +150,7 @@ def test_unified_marching_kernel_and_its_fused_variants(n, analytic, rs):
     x, b = x5[:4 * N], rng.standard_normal(4 * N)
     dg = ops.F.diagonal()
     sweep = lambda v: v + 0.8 * (b - ops.F @ v) / dg
-    kw = dict(rs=rs)
+    kw = dict(rs=rs, re=re)
     assert relerr(emu.stokes_x(0, 0, 0, n, prm, mm, theta, x5, with_p=True, **kw), ops.A @ x5) < 1e-13
     assert relerr(emu.stokes_x(0, 0, 0, n, prm, mm, theta, x, **kw), ops.F @ x) < 1e-13
     assert relerr(emu.stokes_x(0, 1, 0, n, prm, mm, theta, x, b, **kw), b - ops.F @ x) < 1e-13
