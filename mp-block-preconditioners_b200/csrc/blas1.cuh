@@ -169,6 +169,108 @@ __global__ void __launch_bounds__(kRedThreads) k_multi_dot(const double* __restr
   }
 }
 
+struct Alphas {
+  double a[kMaxMulti];
+};
+
+// Two multi-dots in one pass over the basis (low-synchronisation Gram-Schmidt, see gmres_right in plan.cu):
+//   out[k] = <V_k, w>,   out[NV + k] = <V_k, u>,   k < NV      (u = the newest basis vector: its Gram column)
+template <int NV>
+__global__ void __launch_bounds__(kRedThreads) k_multi_dot2(const double* __restrict__ V, size_t ld,
+                                                            const double* __restrict__ w, const double* __restrict__ u,
+                                                            size_t len, double* __restrict__ partial,
+                                                            unsigned int* counter, double* __restrict__ out, RedCtx rc) {
+  __shared__ double smem[kRedThreads / 32];
+  __shared__ double red_sh[kRedMaxVals];
+  double aw[NV], au[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) aw[k] = au[k] = 0.0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < len; i += 2 * stride) {  // two independent rows of loads in flight
+    const double w0 = w[i], w1 = w[i + stride], u0 = u[i], u1 = u[i + stride];
+    double v0[NV], v1[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      v0[k] = V[k * ld + i];
+      v1[k] = V[k * ld + i + stride];
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      aw[k] = fma(v0[k], w0, aw[k]);
+      au[k] = fma(v0[k], u0, au[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      aw[k] = fma(v1[k], w1, aw[k]);
+      au[k] = fma(v1[k], u1, au[k]);
+    }
+  }
+  for (; i < len; i += stride) {
+    const double wi = w[i], ui = u[i];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const double vk = V[k * ld + i];
+      aw[k] = fma(vk, wi, aw[k]);
+      au[k] = fma(vk, ui, au[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double s = block_sum(aw[k], smem);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * 2 * NV + k] = s;
+    const double t = block_sum(au[k], smem);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * 2 * NV + NV + k] = t;
+  }
+  if (last_block(counter)) {
+#pragma unroll
+    for (int k = 0; k < 2 * NV; ++k) {
+      double s = 0.0;
+      for (int bI = threadIdx.x; bI < (int)gridDim.x; bI += blockDim.x) s += partial[(size_t)bI * 2 * NV + k];
+      s = block_sum(s, smem);
+      if (threadIdx.x == 0) red_sh[k] = s;
+    }
+    __syncthreads();
+    p2p_allreduce_sum(rc, red_sh, 2 * NV);
+    if (threadIdx.x < 2 * NV) out[threadIdx.x] = red_sh[threadIdx.x];
+    if (threadIdx.x == 0) *counter = 0u;
+  }
+}
+
+// w -= sum_k h[k] V_k (h by value) fused with nrm = ||w_new|| (only the LAST launch of a chain asks for the norm)
+template <int NV, bool NRM>
+__global__ void __launch_bounds__(kRedThreads) k_multi_axpy_nrm(const double* __restrict__ V, size_t ld, Alphas h,
+                                                                double* __restrict__ w, size_t len,
+                                                                double* __restrict__ partial, unsigned int* counter,
+                                                                double* __restrict__ out_nrm, RedCtx rc) {
+  __shared__ double smem[kRedThreads / 32];
+  __shared__ double red_sh[kRedMaxVals];
+  double acc = 0.0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+    double wi = w[i];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) wi = fma(-h.a[k], V[k * ld + i], wi);
+    w[i] = wi;
+    if (NRM) acc = fma(wi, wi, acc);
+  }
+  if (!NRM) return;
+  const double s = block_sum(acc, smem);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  if (last_block(counter)) {
+    double t = 0.0;
+    for (int bI = threadIdx.x; bI < (int)gridDim.x; bI += blockDim.x) t += partial[bI];
+    t = block_sum(t, smem);
+    if (threadIdx.x == 0) red_sh[0] = t;
+    __syncthreads();
+    p2p_allreduce_sum(rc, red_sh, 1);
+    if (threadIdx.x == 0) {
+      out_nrm[0] = sqrt(red_sh[0]);
+      *counter = 0u;
+    }
+  }
+}
+
 // One fused step of modified Gram-Schmidt (the `for k: h = dot(v_k, w); w -= h v_k` loop of scipy's gmres /
 // the Arnoldi loop of fgmres):   w <- w - alpha_prev * v_prev ;  out_dot = <v_next, w> ;  out_nrm = ||w||^2
 // (each part optional).  4 vector passes per basis vector instead of 5, and the per-thread summation
@@ -325,10 +427,6 @@ __global__ void k_sqrt_inplace(double* v, int nv) {
   const int i = threadIdx.x;
   if (i < nv) v[i] = sqrt(v[i]);
 }
-
-struct Alphas {
-  double a[kMaxMulti];
-};
 
 // y += sum_k alpha[k] * V_k  (alpha by value)
 template <int NV>

@@ -129,6 +129,7 @@ struct mpbp_plan {
   const double* pending_push = nullptr;  // vector whose halo rows the last kernel already pushed
   int coarse_n = 0;  // experimental (MPBP_COARSE=<n>): whole-grid levels with n <= coarse_n run as ONE persistent kernel
   bool fused_mgs = true;
+  bool lowsync = true;  // FGMRES orthogonalisation: low-synchronisation Gram-Schmidt (MPBP_ORTH=mgs: modified Gram-Schmidt)
   int jac_minb = 0;  // __launch_bounds__ min blocks/SM variant of the Jacobi kernel (register cap)
   bool use_graph = true;
   cudaGraphExec_t gexec_apply = nullptr;  // the whole preconditioner apply (vin -> w, t2, xp)
@@ -242,7 +243,7 @@ static void carve(mpbp_plan* p, Bump& B) {
   p->sxc = B.take<double>(n0);
   p->syf = B.take<double>(n0);
   p->syc = B.take<double>(n0);
-  p->partial = B.take<double>((size_t)kMaxRedBlocks * kMaxMulti);
+  p->partial = B.take<double>((size_t)kMaxRedBlocks * 2 * kMaxMulti);
   p->counter = B.take<unsigned int>(64);
   p->scal = B.take<double>(kScal);
   p->dseq = B.take<unsigned long long>(16);
@@ -786,6 +787,58 @@ static int v_mgs(mpbp_plan* p, const double* V, size_t ld, int j, double* w, siz
   return finish(nullptr, nrm_after);
 }
 
+// Low-synchronisation Gram-Schmidt, pass 1: r = V^T w and g = V^T u in ONE pass over the basis (u = newest basis
+// vector).  out_dev: chunks of 8 vectors, chunk c at out_dev + 16c holds [r (nv values) | g (nv values)].
+static int v_multi_dot2(mpbp_plan* p, const double* V, size_t ld, int nvec, const double* w, const double* u, size_t len,
+                        double* out_dev) {
+  const int blocks = (int)std::min<size_t>((len + kRedThreads - 1) / kRedThreads, (size_t)p->red_blocks);
+  for (int k0 = 0, c = 0; k0 < nvec; k0 += kMaxMulti, ++c) {
+    const int nv = std::min(kMaxMulti, nvec - k0);
+    const double* Vk = V + (size_t)k0 * ld;
+    double* o = out_dev + 16 * c;
+    switch (nv) {
+      case 1: k_multi_dot2<1><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, u, len, p->partial, p->counter, o, p->red); break;
+      case 2: k_multi_dot2<2><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, u, len, p->partial, p->counter, o, p->red); break;
+      case 3: k_multi_dot2<3><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, u, len, p->partial, p->counter, o, p->red); break;
+      case 4: k_multi_dot2<4><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, u, len, p->partial, p->counter, o, p->red); break;
+      case 5: k_multi_dot2<5><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, u, len, p->partial, p->counter, o, p->red); break;
+      case 6: k_multi_dot2<6><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, u, len, p->partial, p->counter, o, p->red); break;
+      case 7: k_multi_dot2<7><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, u, len, p->partial, p->counter, o, p->red); break;
+      default: k_multi_dot2<8><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, w, u, len, p->partial, p->counter, o, p->red); break;
+    }
+    LAUNCH_CHECK(p);
+  }
+  return 0;
+}
+// pass 2: w -= V h (h on the host), nrm_dev = ||w_new|| (summed over ranks inside the kernel)
+static int v_multi_axpy_nrm(mpbp_plan* p, const double* V, size_t ld, int nvec, const double* h_host, double* w, size_t len,
+                            double* nrm_dev) {
+  const int blocks = (int)std::min<size_t>((len + kRedThreads - 1) / kRedThreads, (size_t)p->red_blocks);
+  for (int k0 = 0; k0 < nvec; k0 += kMaxMulti) {
+    const int nv = std::min(kMaxMulti, nvec - k0);
+    const bool last = k0 + nv >= nvec;
+    Alphas al{};
+    for (int k = 0; k < nv; ++k) al.a[k] = h_host[k0 + k];
+    const double* Vk = V + (size_t)k0 * ld;
+#define MPBP_AXN(NV)                                                                                                        \
+  if (last) k_multi_axpy_nrm<NV, true><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, al, w, len, p->partial, p->counter, nrm_dev, p->red); \
+  else k_multi_axpy_nrm<NV, false><<<blocks, kRedThreads, 0, p->st>>>(Vk, ld, al, w, len, p->partial, p->counter, nrm_dev, p->red);
+    switch (nv) {
+      case 1: MPBP_AXN(1) break;
+      case 2: MPBP_AXN(2) break;
+      case 3: MPBP_AXN(3) break;
+      case 4: MPBP_AXN(4) break;
+      case 5: MPBP_AXN(5) break;
+      case 6: MPBP_AXN(6) break;
+      case 7: MPBP_AXN(7) break;
+      default: MPBP_AXN(8) break;
+    }
+#undef MPBP_AXN
+    LAUNCH_CHECK(p);
+  }
+  return 0;
+}
+
 // fetch `count` device scalars to the pinned host mirror (synchronises the stream)
 static int fetch_scal(mpbp_plan* p, const double* dev, int count, double* host) {
   CU(cudaMemcpyAsync(host, dev, count * sizeof(double), cudaMemcpyDeviceToHost, p->st));
@@ -1276,6 +1329,7 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
   if (const char* e = getenv("MPBP_GRAPH")) p->use_graph = atoi(e) != 0;
   if (const char* e = getenv("MPBP_JAC_MINB")) p->jac_minb = atoi(e);
   if (const char* e = getenv("MPBP_FUSED_MGS")) p->fused_mgs = atoi(e) != 0;
+  if (const char* e = getenv("MPBP_ORTH")) p->lowsync = strcmp(e, "mgs") != 0;
   if (const char* e = getenv("MPBP_FUSE")) p->fuse = atoi(e);
   if (const char* e = getenv("MPBP_COARSE")) p->coarse_n = atoi(e);
   if (const char* e = getenv("MPBP_PUSH_FUSED")) p->push_fused = atoi(e) != 0;
@@ -1366,7 +1420,9 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
       if (const char* e = getenv("MPBP_PF")) v.geo.pf = std::max(0, std::min(atoi(e), 64));
       v.geo4 = v.geo;
       v.geoL = v.geo;
-      const bool wave = !(getenv("MPBP_WAVE") && atoi(getenv("MPBP_WAVE")) == 0);
+      // single-wave decomposition (set_strips): measured SLOWER than uniform 32-row strips on one B200 at 4096^2
+      // (Jacobi sweep 0.344 ms vs 0.290 ms, profiles/r2_tuning.txt) -- off unless MPBP_WAVE=1
+      const bool wave = getenv("MPBP_WAVE") && atoi(getenv("MPBP_WAVE")) != 0;
       if (wave) {
         set_strips(v.geo, gx, v.rows, 5 * sms_);
         set_strips(v.geo4, gx, v.rows, 4 * sms_);
@@ -2018,6 +2074,9 @@ static int gmres_right(mpbp_plan* p, const double* b, double* x, const mpbp_gmre
   p->last_H.assign((size_t)(m + 1) * m, 0.0);
   p->last_m = m;
   p->last_k = 0;
+  // low-synchronisation orthogonalisation needs the all-reduce inside the kernels (or a single rank)
+  const bool lowsync = p->lowsync && (p->nranks == 1 || p->red.nranks > 1);
+  std::vector<double> Lg((size_t)m * m, 0.0), hcoef(m + 1, 0.0);
   int it = 0;
   bool first = true;
   bool stop = false;
@@ -2044,10 +2103,37 @@ static int gmres_right(mpbp_plan* p, const double* b, double* x, const mpbp_gmre
       double* zj = Z + (size_t)j * len;
       RET(psolve(p, pc, vj, zj, len));                       // Z_j = M v_j
       RET(op_stokes(p, 0, 0, true, zj, nullptr, w, 0.0));    // w = A Z_j
-      RET(v_mgs(p, V, len, j, w, len, ds, ds + j + 1, nullptr));
-      k_scale_dev<<<ew_blocks(len), 256, 0, p->st>>>(ds + j + 1, 1, w, V + (size_t)(j + 1) * len, len);
-      LAUNCH_CHECK(p);
-      RET(fetch_scal(p, ds, j + 2, hs));
+      if (lowsync) {
+        // Low-synchronisation modified Gram-Schmidt: ONE pass over the basis computes r = V^T w together with the
+        // Gram column g = V^T v_j of the newest basis vector; with L = strictly lower part of V^T V the MGS
+        // coefficients are the forward substitution (I + L) h = r (h_k = <v_k, w - sum_{i<k} h_i v_i> exactly), and a
+        // second pass applies w -= V h and returns ||w||.  2j+6 vector passes and 2 reductions per iteration instead
+        // of 4j+6 passes and j+2 reductions.
+        const int nc = (j + 1 + kMaxMulti - 1) / kMaxMulti;
+        RET(v_multi_dot2(p, V, len, j + 1, w, vj, len, ds));
+        RET(fetch_scal(p, ds, 16 * nc, hs));
+        for (int k = 0; k <= j; ++k) {
+          const int c = k / kMaxMulti, o = k % kMaxMulti, nv = std::min(kMaxMulti, j + 1 - c * kMaxMulti);
+          hcoef[k] = hs[16 * c + o];
+          if (k < j) Lg[(size_t)j * m + k] = hs[16 * c + nv + o];  // <v_k, v_j>
+        }
+        for (int k = 0; k <= j; ++k) {
+          double sacc = hcoef[k];
+          for (int i = 0; i < k; ++i) sacc -= Lg[(size_t)k * m + i] * hcoef[i];
+          hcoef[k] = sacc;
+        }
+        RET(v_multi_axpy_nrm(p, V, len, j + 1, hcoef.data(), w, len, ds));
+        k_scale_dev<<<ew_blocks(len), 256, 0, p->st>>>(ds, 1, w, V + (size_t)(j + 1) * len, len);
+        LAUNCH_CHECK(p);
+        RET(fetch_scal(p, ds, 1, hs));
+        hs[j + 1] = hs[0];
+        for (int i = 0; i <= j; ++i) hs[i] = hcoef[i];
+      } else {
+        RET(v_mgs(p, V, len, j, w, len, ds, ds + j + 1, nullptr));
+        k_scale_dev<<<ew_blocks(len), 256, 0, p->st>>>(ds + j + 1, 1, w, V + (size_t)(j + 1) * len, len);
+        LAUNCH_CHECK(p);
+        RET(fetch_scal(p, ds, j + 2, hs));
+      }
       for (int i = 0; i <= j + 1; ++i) Hm(i, j) = hs[i];
       if (j == 0) std::fill(p->last_H.begin(), p->last_H.end(), 0.0);
       for (int i = 0; i <= j + 1; ++i) p->last_H[(size_t)i * m + j] = hs[i];

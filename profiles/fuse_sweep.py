@@ -31,9 +31,10 @@ def timeit(fn, reps=5):
     return e0.elapsed_time(e1) / reps
 
 
-KNOBS = ("MPBP_FUSE", "MPBP_GRAPH", "MPBP_COARSE", "MPBP_PF", "MPBP_WAVE")
-for env in [dict(), dict(MPBP_WAVE="0"), dict(MPBP_FUSE="1"), dict(MPBP_FUSE="3"), dict(MPBP_FUSE="5"),
-            dict(MPBP_GRAPH="0"), dict(MPBP_COARSE="64"), dict(MPBP_PF="2"), dict(MPBP_PF="4"), dict(MPBP_PF="6")]:
+KNOBS = ("MPBP_FUSE", "MPBP_GRAPH", "MPBP_COARSE", "MPBP_PF", "MPBP_WAVE", "MPBP_RS")
+for env in [dict(), dict(MPBP_WAVE="1"), dict(MPBP_FUSE="1"), dict(MPBP_FUSE="3"), dict(MPBP_FUSE="5"),
+            dict(MPBP_GRAPH="0"), dict(MPBP_COARSE="64"), dict(MPBP_PF="2"), dict(MPBP_PF="4"), dict(MPBP_PF="5"),
+            dict(MPBP_RS="16"), dict(MPBP_RS="24"), dict(MPBP_RS="48")]:
     for k in KNOBS:
         os.environ.pop(k, None)
     os.environ.update(env)

@@ -217,11 +217,18 @@ def test_unpreconditioned_matches_oracle(mp):
     assert info != 0 and info_o != 0
     h, ho = mp.fgmres.last_history, O.fgmres.last_history.copy()
     assert len(h) == len(ho) == 100
-    # conditioning of the oracle's own history under 1-ulp perturbations of b
+    # conditioning of the oracle's own history: 16 re-runs under the rounding model (every A.x returns
+    # y_i + u sqrt(k_i) (|A||x|)_i N(0,1), oracle/mpbp_oracle.py:mv) with 1-ulp perturbations of b
+    import scipy.sparse.linalg as spla
     sens = np.zeros(100)
     prng = np.random.default_rng(5)
-    for _ in range(16):
-        O.fgmres(ops.A, b_vec * (1 + 1.2e-16 * prng.standard_normal(b_vec.shape)), M=None, tol=1e-8, maxiter=100)
+    Aop = spla.LinearOperator(ops.A.shape, dtype=np.float64, matvec=lambda z: O.mv(ops.A, z))
+    for i in range(16):
+        O.set_rounding_model(1.1e-16, seed=500 + i)
+        try:
+            O.fgmres(Aop, b_vec * (1 + 1.2e-16 * prng.standard_normal(b_vec.shape)), M=None, tol=1e-8, maxiter=100)
+        finally:
+            O.set_rounding_model(0.0)
         sens = np.maximum(sens, np.abs(O.fgmres.last_history - ho) / ho)
     hist_check(h, ho, sens, label="unpreconditioned")
     assert np.allclose(h[:20], ho[:20], rtol=1e-9)
