@@ -254,12 +254,20 @@ def run_gpu(args):
     jac()
     ms_jac = timed(jac) / sweeps
     jac_bytes = 104.0 * N
-    roof = {"bound": "hbm", "kernel": "k_stokes<2,false> (damped-Jacobi sweep on F, level 0)",
+    roof = {"bound": "hbm", "kernel": "k_stokes_x<IN 0, MODE 2, EP 0> (damped-Jacobi sweep on F, level 0)",
             "achieved": jac_bytes / (ms_jac * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
-            "bytes_per_launch": jac_bytes, "ms_per_launch": ms_jac,
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 4096^2 on one GPU (ncu --set full,
-            # profiles/r1_ncu_k_stokes_jacobi.txt): 1.2557 GB + 0.5139 GB = 1.014 x the algorithmic bytes
-            "traffic": 1.7696e9 if (world == 1 and n == 4096) else None}
+            "bytes_per_launch": jac_bytes, "ms_per_launch": ms_jac, "traffic": None}
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch of THIS kernel from the committed ncu --set full capture
+    # of the final code (profiles/r2_ncu_traffic.json, written by profiles/ncu_table.py); only quoted for the
+    # configuration it was captured on
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")) as f:
+            tr = json.load(f)
+        if world == 1 and n == int(tr["n"]):
+            roof["traffic"] = float(tr["dram_bytes_read"]) + float(tr["dram_bytes_write"])
+            roof["traffic_source"] = tr.get("source", "profiles/r2_ncu_traffic.json")
+    except Exception:
+        pass
     roof["frac"] = roof["achieved"] / peak
 
     # ---- the preconditioner apply as a whole and the other hot kernels ----
