@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ll.cuh"
+
 namespace mpbp {
 
 constexpr int kRedThreads = 256;
@@ -63,51 +65,43 @@ __device__ __forceinline__ bool last_block(unsigned int* counter) {
 
 // ---------------------------------------------------------------------------------------------------------
 // All-reduce (sum) of a few scalars over the ranks through peer memory, fused into the reduction kernels: the last
-// block of the local reduction stores its partial sums into EVERY rank's comm buffer (NVLink peer stores), releases
-// a per-(slot, source rank) flag there, waits until all ranks' contributions have arrived in its own buffer and adds
-// them in rank order -- the result is bitwise identical on all ranks and no NCCL kernel is launched (an 8-byte
-// ncclAllReduce costs 10-20 us, j+2 of them per Arnoldi step).  Operation number *rseq (the same on all ranks)
-// alternates between two slots; a rank can only reach operation k+2 after it has seen every rank's flag of k+1,
-// which each rank released after it had finished reading slot k&1.
+// block of the local reduction stores its partial sums into EVERY rank's comm buffer (NVLink peer stores) as LL
+// elements (value + operation number in one 16-byte store, ll.cuh), polls its own buffer until all ranks' elements of
+// this operation have arrived and adds them in rank order -- the result is bitwise identical on all ranks, no NCCL
+// kernel is launched (an 8-byte ncclAllReduce costs 10-20 us) and no memory fence sits on the critical path.
+// Operation number *rseq (the same on all ranks) alternates between two slots; a rank can only reach operation k+2
+// after it has received every rank's elements of k+1, which each rank sent after it had finished reading slot k&1.
 constexpr int kRedMaxVals = 16;
 constexpr int kRedMaxRanks = 8;
-constexpr size_t kRedBytes = 4096;
+constexpr size_t kRedBytes = 2 * kRedMaxRanks * kRedMaxVals * sizeof(LLElem);
 struct RedCtx {
   char* peers[kRedMaxRanks];  // every rank's reduction area (mapped peer memory); peers[rank] is this rank's own
   int rank, nranks;           // nranks <= 1: no exchange
   unsigned long long* rseq;   // device-resident operation counter
 };
-__device__ __forceinline__ unsigned long long* red_flag(char* area, int slot, int src) {
-  return reinterpret_cast<unsigned long long*>(area) + slot * kRedMaxRanks + src;
+__device__ __forceinline__ LLElem* red_vals(char* area, int slot, int src) {
+  return reinterpret_cast<LLElem*>(area) + (size_t)(slot * kRedMaxRanks + src) * kRedMaxVals;
 }
-__device__ __forceinline__ double* red_vals(char* area, int slot, int src) {
-  return reinterpret_cast<double*>(area + 256) + (size_t)(slot * kRedMaxRanks + src) * kRedMaxVals;
-}
-// called by every thread of ONE block; vals: `count` block-visible doubles (shared memory), overwritten by the sums
+// called by every thread of ONE block (>= nranks * count threads); vals: `count` block-visible doubles (shared
+// memory), overwritten by the sums
 __device__ __forceinline__ void p2p_allreduce_sum(const RedCtx& rc, double* vals, int count) {
   if (rc.nranks <= 1) return;
+  __shared__ double red_in[kRedMaxRanks * kRedMaxVals];
   const unsigned long long seq = *rc.rseq + 1ull;
   const int slot = (int)(seq & 1ull);
   const int t = threadIdx.x;
+  int r = 0, i = 0;
   if (t < rc.nranks * count) {
-    const int r = t / count, i = t - r * count;
-    red_vals(rc.peers[r], slot, rc.rank)[i] = vals[i];
+    r = t / count;
+    i = t - r * count;
+    st_ll(red_vals(rc.peers[r], slot, rc.rank) + i, vals[i], seq);
   }
-  __threadfence_system();
   __syncthreads();
-  if (t < rc.nranks) {
-    unsigned long long* f = red_flag(rc.peers[t], slot, rc.rank);
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(seq) : "memory");
-    const unsigned long long* mine = red_flag(rc.peers[rc.rank], slot, t);
-    unsigned long long got;
-    do {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(mine) : "memory");
-    } while (got < seq);
-  }
+  if (t < rc.nranks * count) red_in[r * count + i] = ll_wait(red_vals(rc.peers[rc.rank], slot, r) + i, seq);
   __syncthreads();
   if (t < count) {
     double s = 0.0;
-    for (int r = 0; r < rc.nranks; ++r) s += __ldcg(red_vals(rc.peers[rc.rank], slot, r) + t);
+    for (int q = 0; q < rc.nranks; ++q) s += red_in[q * count + t];
     vals[t] = s;
   }
   __syncthreads();

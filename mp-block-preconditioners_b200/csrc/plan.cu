@@ -64,7 +64,8 @@ struct Level {
   Geo geoL{};  // strip geometry for the light kernels (k_poisson, k_div, k_grad, k_jacobi0_F: 12-16 blocks/SM)
   Phys ph{};
   double* th = nullptr;    // padded theta: (rows+2) x n
-  double* halo = nullptr;  // [2][5][n] receive rows (dist only)
+  double* halo = nullptr;  // [2][5][n] receive rows (dist only): NCCL halos; peer-memory mode: the static stash of x's rows
+  double* hland = nullptr; // [2][5][n] transient landing buffer of the rows fetched from the comm buffer (dist only)
   double *bF = nullptr, *xF = nullptr, *tF = nullptr, *rF = nullptr;  // 4*rows*n each
   double *bP = nullptr, *xP = nullptr, *tP = nullptr, *rP = nullptr;  // rows*n each
   double *gF = nullptr, *gP = nullptr;  // restricted slab before the all-gather (first replicated level only)
@@ -199,6 +200,7 @@ static void carve(mpbp_plan* p, Bump& B) {
     const size_t fs = v.fs();
     v.th = B.take<double>((size_t)(v.rows + 2) * v.n);
     v.halo = v.dist ? B.take<double>((size_t)2 * 5 * v.n) : nullptr;
+    v.hland = v.dist ? B.take<double>((size_t)2 * 5 * v.n) : nullptr;
     v.tF = B.take<double>(4 * fs);
     v.rF = B.take<double>(4 * fs);
     v.tP = B.take<double>(fs);
@@ -348,7 +350,7 @@ static int fetch_static_halo(mpbp_plan* p, Level& v, const double* x, int nf, do
 }
 
 // view of a level vector for stencil kernels (performs the halo exchange when distributed)
-static int make_view(mpbp_plan* p, Level& v, const double* x, int nf, VecIn& out) {
+static int make_view(mpbp_plan* p, Level& v, const double* x, int nf, VecIn& out, bool stash = false) {
   const size_t fs = v.fs();
   out.x = x;
   out.fs = fs;
@@ -361,7 +363,9 @@ static int make_view(mpbp_plan* p, Level& v, const double* x, int nf, VecIn& out
       out.dseq = p->dseq;
       out.comm = p->comm_local;
       out.area = p->comm_area;
-      out.top = out.bot = nullptr;  // resolved on the device from *dseq
+      out.land = stash ? v.halo : v.hland;  // the consumer's edge strips land the fetched rows here ...
+      out.top = out.land;                    // ... and read them back through the ordinary halo pointers
+      out.bot = out.land + 5 * (size_t)v.n;
     } else {
       out.top = v.halo;
       out.bot = v.halo + 5 * (size_t)v.n;
@@ -432,8 +436,7 @@ static int op_stokes(mpbp_plan* p, int l, int mode, bool with_p, const double* x
                      double omega, const ChebEp* ce = nullptr, bool stash = false) {
   Level& v = p->lev[l];
   StokesArgs a{};
-  RET(make_view(p, v, x, with_p ? 5 : 4, a.xin));
-  if (stash && v.dist && p->p2p) a.stash = v.halo;
+  RET(make_view(p, v, x, with_p ? 5 : 4, a.xin, stash));
   a.b = b;
   a.y = y;
   a.omega = omega;
@@ -1235,7 +1238,7 @@ static int build_coarse_inverses(mpbp_plan* p) {
 static int setup_p2p(mpbp_plan* p) {
   const int P = p->nranks, prev = (p->rank + P - 1) % P, next = (p->rank + 1) % P;
   p->comm_area = (size_t)5 * p->lev[0].n;
-  const size_t halo_bytes = (kFlagBytes + 4 * p->comm_area * sizeof(double) + 255) & ~size_t(255);
+  const size_t halo_bytes = (comm_halo_bytes(p->comm_area) + 255) & ~size_t(255);
   const size_t bytes = halo_bytes + kRedBytes;
   CU(cudaMalloc(&p->comm_local, bytes));
   CU(cudaMemset(p->comm_local, 0, bytes));
@@ -1676,7 +1679,7 @@ extern "C" int mpbp_comm_probe(mpbp_plan* p, int reps, double* halo_us, double* 
         p->pending_push = nullptr;
         RET(make_view(p, v, p->vin, 5, in));
         if (p->p2p) {
-          k_halo_consume<<<1, 32, 0, p->st>>>(in, p->scal + kScal - 2);
+          k_halo_consume<<<(v.n + 255) / 256, 256, 0, p->st>>>(in, 5, v.n, p->scal + kScal - 2);
           LAUNCH_CHECK(p);
         }
       }

@@ -20,6 +20,8 @@
 #endif
 #include <stdint.h>
 
+#include "ll.cuh"
+
 namespace mpbp {
 
 constexpr int kWarpCols = 30;   // output columns per warp
@@ -44,129 +46,102 @@ struct VecIn {
   const double* top;
   const double* bot;
   size_t fs, hs;
-  // multi-GPU: the halo rows are pushed into this rank's comm buffer by the ring neighbours (peer stores
-  // over NVLink).  The exchange sequence number lives on the device (`dseq`, bumped by k_halo_push), so
-  // kernel arguments never change between calls and whole V-cycles replay as CUDA graphs.  A kernel first
-  // resolves slot/top/bot/flags from *dseq; edge warps then wait until the neighbour's flag reaches it.
+  // multi-GPU: the halo rows are pushed into this rank's comm buffer by the ring neighbours (peer stores over
+  // NVLink) as (value, sequence tag) pairs.  The exchange sequence number lives on the device (`dseq`, bumped by the
+  // pushing kernel), so kernel arguments never change between calls and whole applies replay as CUDA graphs.  The
+  // threads of a consumer's edge strips poll the elements they need until the tag matches, land the values in the
+  // plain per-level buffer `land` ([2][5][n]: top rows, then bottom rows) and read them from there: the host sets
+  // top = land, bot = land + 5n, hs = n, so the view is never modified on the device (its fields stay kernel-parameter
+  // constants on the uniform datapath).
   const unsigned long long* dseq;   // null: single GPU / replicated level (top/bot given directly)
   char* comm;                       // this rank's comm buffer
-  size_t area;                      // doubles per (slot, direction) halo area
-  const unsigned long long* flag_top;
-  const unsigned long long* flag_bot;
-  unsigned long long seq;
+  size_t area;                      // elements per (slot, direction) halo area
+  double* land;                     // landing buffer of the fetched rows
 };
 
-// comm buffer layout: 4 flags (slot x {top,bot}), 128 B apart, then [slot][dir][5 fields][n0] doubles
-constexpr size_t kFlagStride = 128;
-constexpr size_t kFlagBytes = 4 * kFlagStride;
-__host__ __device__ __forceinline__ unsigned long long* comm_flag(char* base, int slot, int dir) {
-  return reinterpret_cast<unsigned long long*>(base + (size_t)(slot * 2 + dir) * kFlagStride);
+// ---- LL halo protocol ---------------------------------------------------------------------------------------------
+// Every 8-byte value travels with its 8-byte sequence tag in ONE 16-byte store (the idea of NCCL's LL protocol): a
+// consumer that reads a matching tag has the value, so the exchange needs no memory fence, no flag and no "last block"
+// ticket on the critical path -- measured 3 us per back-to-back exchanging kernel against 10-13 us for data stores +
+// __threadfence_system + release flag (profiles/micro/halo_latency.cu).
+// Exchange number s (identical on all ranks: every rank runs the same kernel sequence) lives in slot s % 3 of the
+// receiver's comm buffer, layout [slot][dir][5 fields * n0] elements.  Rules:
+//  * consumer: a thread reading exchange s polls its elements until tag == s;
+//  * producer (credit): before a block writes exchange q into neighbour X's slot q % 3 -- which still holds q-3 -- it
+//    waits until SOME element of X's exchange q-1 has arrived here.  X's kernel producing q-1 has then started, so every
+//    earlier kernel of X has completed, in particular the producer of q-2 and with it every reader of q-3 (readers of
+//    q-3 are at or before the producer of q-2; the producer of q-1 may itself still be reading q-2, hence three slots).
+//    X cannot overwrite q-1 with q+2 before it has seen this rank's q+1, so the tag is exact.
+constexpr int kHaloSlots = 3;
+__host__ __device__ __forceinline__ size_t comm_halo_bytes(size_t area) { return (size_t)kHaloSlots * 2 * area * sizeof(LLElem); }
+__host__ __device__ __forceinline__ LLElem* comm_halo(char* base, size_t area, int slot, int dir) {
+  return reinterpret_cast<LLElem*>(base) + (size_t)(slot * 2 + dir) * area;
 }
-__host__ __device__ __forceinline__ double* comm_halo(char* base, size_t area, int slot, int dir) {
-  return reinterpret_cast<double*>(base + kFlagBytes) + (size_t)(slot * 2 + dir) * area;
-}
-__device__ __forceinline__ void resolve_halo(VecIn& v) {
-  if (v.dseq == nullptr) return;
-  const unsigned long long s = *v.dseq;
-  const int slot = (int)(s & 1ull);
-  v.seq = s;
-  v.top = comm_halo(v.comm, v.area, slot, 0);
-  v.bot = comm_halo(v.comm, v.area, slot, 1);
-  v.flag_top = comm_flag(v.comm, slot, 0);
-  v.flag_bot = comm_flag(v.comm, slot, 1);
-}
-
-#ifdef MPBP_EMU
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  return *(const volatile unsigned long long*)p;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  *(volatile unsigned long long*)p = v;
-}
-#else
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-#endif
-// Halo protocol.  Exchange number s (identical on all ranks: every rank runs the same kernel sequence) lives in
-// slot s&1 of the receiver's comm buffer; the receiver's flag (slot, dir) holds the newest sequence the neighbour
-// on that side has fully written.  Two rules make slot reuse safe for any number of ranks:
-//  * consumer: a kernel reading exchange s waits (edge strips only) until flag(s&1, dir) >= s;
-//  * producer (credit): before writing exchange q into neighbour X's slot q&1 -- which still holds q-2 -- the
-//    producer waits until X's flag for q-1 has arrived HERE.  X released that flag from a kernel that is
-//    stream-ordered after every kernel of X that read q-2 (at most one exchange is outstanding), so X is done
-//    with the slot.  No cycle: X's push q-1 itself only needs this rank's q-2, sent long ago.
-// The credit makes the protocol independent of which sides a consumer happens to read, and of pushes that are
-// never consumed (a fused push whose result the next kernel does not need).
-__device__ __forceinline__ void halo_credit(char* my_comm, unsigned long long q, bool to_prev, bool to_next) {
-  if (q < 2ull) return;
-  const int slot = (int)((q - 1ull) & 1ull);
-  if (to_prev)
-    while (ld_acquire_sys(comm_flag(my_comm, slot, 0)) < q - 1ull) {
-    }
-  if (to_next)
-    while (ld_acquire_sys(comm_flag(my_comm, slot, 1)) < q - 1ull) {
-    }
-}
-// warp-level wait for the neighbours' halo rows (called by whole warps; lane 0 polls)
-__device__ __forceinline__ void halo_wait(VecIn& v, bool need_top, bool need_bot) {
-  if (v.dseq == nullptr) return;
-  resolve_halo(v);
-  if ((threadIdx.x & 31) == 0) {
-    if (need_top)
-      while (ld_acquire_sys(v.flag_top) < v.seq) {
-      }
-    if (need_bot)
-      while (ld_acquire_sys(v.flag_bot) < v.seq) {
-      }
+// One thread fetches the halo elements of column `col` (fields k0, k0 + kstep, ... < k0 + nk * kstep; row length n) that
+// IT will read and lands them in `land`; the same thread reads them back later (program order), so no barrier is
+// involved.  WARP: called by all 32 lanes of a warp with warp-uniform arguments except `col` (warp-uniform wait loop).
+template <bool WARP>
+__device__ __forceinline__ void halo_fetch_cols(double* land, char* comm, size_t area, const unsigned long long* dseq, int k0,
+                                              int nk, int kstep, int n, int col, bool need_top, bool need_bot) {
+  const unsigned long long s = *dseq;
+  const int slot = (int)(s % (unsigned long long)kHaloSlots);
+  const LLElem* ll_top = comm_halo(comm, area, slot, 0);
+  const LLElem* ll_bot = comm_halo(comm, area, slot, 1);
+#pragma unroll 1
+  for (int i = 0, k = k0; i < nk; ++i, k += kstep) {
+    const int e = k * n + col;
+    if (need_top) land[e] = WARP ? ll_wait_warp(ll_top + e, s) : ll_wait(ll_top + e, s);
+    if (need_bot) land[e + 5 * n] = WARP ? ll_wait_warp(ll_bot + e, s) : ll_wait(ll_bot + e, s);
   }
-  __syncwarp();
+}
+template <bool WARP = false>
+__device__ __forceinline__ void halo_fetch(const VecIn& v, int k0, int nk, int kstep, int n, int col, bool need_top,
+                                           bool need_bot) {
+  if (v.dseq != nullptr) halo_fetch_cols<WARP>(v.land, v.comm, v.area, v.dseq, k0, nk, kstep, n, col, need_top, need_bot);
+}
+// producer credit (see above): lane 0 of a pushing warp, before its first remote store of exchange q
+__device__ __forceinline__ void halo_credit(char* my_comm, size_t area, unsigned long long q, bool to_prev, bool to_next) {
+  if (q < 2ull) return;
+  const int slot = (int)((q - 1ull) % (unsigned long long)kHaloSlots);
+  if (to_prev) ll_wait(comm_halo(my_comm, area, slot, 0), q - 1ull);
+  if (to_next) ll_wait(comm_halo(my_comm, area, slot, 1), q - 1ull);
 }
 
-// Halo push: copies this rank's first / last slab row of every field into the ring neighbours' halo
-// buffers (peer memory over NVLink) and then releases their flags.  One thread per (field, column);
-// the last block to finish publishes the flags.  Replaces an ncclSend/ncclRecv pair per field and
-// direction.
+// Halo push: copies this rank's first / last slab row of every field into the ring neighbours' halo areas (peer
+// memory over NVLink).  One thread per (field, column).  Used where the producer of a vector is not a stencil kernel.
 __global__ void __launch_bounds__(256) k_halo_push(const double* __restrict__ x, int nf, size_t fs, int rows, int n,
                                                    char* prev_comm, char* next_comm, char* my_comm, size_t area,
                                                    unsigned long long* dseq, unsigned int* done_counter) {
   const unsigned long long seq = *dseq + 1ull;  // read before this block's ticket, written only by the last block
-  const int slot = (int)(seq & 1ull);
-  if (threadIdx.x == 0) halo_credit(my_comm, seq, true, true);
+  const int slot = (int)(seq % (unsigned long long)kHaloSlots);
+  if (threadIdx.x == 0) halo_credit(my_comm, area, seq, true, true);
   __syncthreads();
-  double* __restrict__ prev_bot = comm_halo(prev_comm, area, slot, 1);
-  double* __restrict__ next_top = comm_halo(next_comm, area, slot, 0);
+  LLElem* prev_bot = comm_halo(prev_comm, area, slot, 1);
+  LLElem* next_top = comm_halo(next_comm, area, slot, 0);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nf * n) {
     const int k = i / n, c = i - k * n;
-    const double first = x[k * fs + c];
-    const double last = x[k * fs + (size_t)(rows - 1) * n + c];
-    prev_bot[i] = first;  // my first row is the previous rank's row `rows`
-    next_top[i] = last;   // my last row is the next rank's row -1
+    st_ll(prev_bot + i, x[k * fs + c], seq);                          // my first row is the previous rank's row `rows`
+    st_ll(next_top + i, x[k * fs + (size_t)(rows - 1) * n + c], seq);  // my last row is the next rank's row -1
   }
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int t = atomicAdd(done_counter, 1u);
     if (t == gridDim.x - 1) {
       *done_counter = 0u;
       *dseq = seq;
-      __threadfence_system();
-      st_release_sys(comm_flag(prev_comm, slot, 1), seq);
-      st_release_sys(comm_flag(next_comm, slot, 0), seq);
     }
   }
 }
 
 // consumer side of one halo exchange and nothing else (communication probe: exchange latency without a stencil)
-__global__ void k_halo_consume(VecIn v, double* sink) {
-  halo_wait(v, true, true);
-  if (threadIdx.x == 0 && sink) sink[0] = v.top[0] + v.bot[0];
+__global__ void k_halo_consume(VecIn v, int nf, int n, double* sink) {
+  double acc = 0.0;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+    halo_fetch(v, 0, nf, 1, n, c, true, true);
+    acc += v.land[c];
+  }
+  if (sink && acc == 1.2345e300) sink[0] = acc;
 }
 
 // Chebyshev epilogue of the last smoothing sweep of a V-cycle: the sweep's result is the cycle's output z, which is
@@ -255,37 +230,35 @@ __device__ __forceinline__ LaneGeom lane_geom(int n) {
   return g;
 }
 
-// Fused halo push (MPBP_PUSH_FUSED): the producing stencil kernel itself stores its first and
-// last output rows into the ring neighbours' comm buffers (peer memory over NVLink) and the last block of each
-// edge strip releases that direction's flag -- the compute kernel IS the halo exchange, and because the edge
-// strips are scheduled first the transfer overlaps the interior of the slab.
+// Fused halo push (MPBP_PUSH_FUSED): the producing stencil kernel itself stores its first and last output rows into
+// the ring neighbours' comm buffers (peer memory over NVLink, LL elements) -- the compute kernel IS the halo exchange,
+// and because the edge strips are scheduled first the transfer overlaps the interior of the slab.
 struct PushOut {
   char* prev_comm;            // neighbours' comm buffers (mapped peer memory)
   char* next_comm;
-  char* my_comm;              // this rank's comm buffer (credit flags)
-  size_t area;                // doubles per (slot, direction) halo area
+  char* my_comm;              // this rank's comm buffer (credit)
+  size_t area;                // elements per (slot, direction) halo area
   unsigned long long* dseq;   // this rank's exchange counter: output rows go out under sequence *dseq + 1
-  unsigned int* counters;     // [0] first-strip blocks done, [1] last-strip blocks done, [2] all edge blocks done
+  unsigned int* counters;     // [2] edge blocks done
 };
 
 // A producing kernel's fused push.  Blocks that own the slab's first row (`first`) write it into the previous
-// rank's bottom halo area, blocks that own the last row (`last`) into the next rank's top area, both under
-// sequence *dseq + 1; the last such block per direction releases the neighbour's flag and the last edge block of
-// the launch bumps *dseq.  push_begin: every warp of an edge block (credit wait before the first remote store);
-// push_end: every non-exited thread of an edge block, after its last remote store.
+// rank's bottom halo area, blocks that own the last row (`last`) into the next rank's top area, both tagged with
+// sequence *dseq + 1; the last edge block of the launch bumps *dseq.  push_begin: every warp of an edge block (credit
+// wait before the first remote store); push_end: every non-exited thread of an edge block.
 struct PushCtx {
-  double* prev;  // neighbour's bot area: receives my row 0
-  double* next;  // neighbour's top area: receives my row rows-1
+  LLElem* prev;  // neighbour's bot area: receives my row 0
+  LLElem* next;  // neighbour's top area: receives my row rows-1
   unsigned long long seq;
 };
 __device__ __forceinline__ PushCtx push_begin(const PushOut& po, bool first, bool last) {
   PushCtx c;
   c.seq = *po.dseq + 1ull;  // bumped only after every edge block of this launch has finished
-  const int slot = (int)(c.seq & 1ull);
+  const int slot = (int)(c.seq % (unsigned long long)kHaloSlots);
   c.prev = comm_halo(po.prev_comm, po.area, slot, 1);
   c.next = comm_halo(po.next_comm, po.area, slot, 0);
   if (first || last) {
-    if ((threadIdx.x & 31) == 0) halo_credit(po.my_comm, c.seq, first, last);
+    if ((threadIdx.x & 31) == 0) halo_credit(po.my_comm, po.area, c.seq, first, last);
     __syncwarp();
   }
   return c;
@@ -294,20 +267,8 @@ __device__ __forceinline__ PushCtx push_begin(const PushOut& po, bool first, boo
 __device__ __forceinline__ void push_end(const PushOut& po, const PushCtx& c, bool first, bool last, unsigned int n_first,
                                          unsigned int n_last, bool same_blocks) {
   if (!(first || last)) return;
-  __threadfence_system();
-  __syncthreads();
+  __syncthreads();  // every warp of the block has read *dseq
   if (threadIdx.x == 0) {
-    const int slot = (int)(c.seq & 1ull);
-    if (first && atomicAdd(&po.counters[0], 1u) == n_first - 1) {
-      po.counters[0] = 0u;
-      __threadfence_system();
-      st_release_sys(comm_flag(po.prev_comm, slot, 1), c.seq);
-    }
-    if (last && atomicAdd(&po.counters[1], 1u) == n_last - 1) {
-      po.counters[1] = 0u;
-      __threadfence_system();
-      st_release_sys(comm_flag(po.next_comm, slot, 0), c.seq);
-    }
     const unsigned int total = same_blocks ? n_first : n_first + n_last;
     if (atomicAdd(&po.counters[2], 1u) == total - 1) {
       po.counters[2] = 0u;
@@ -426,7 +387,9 @@ __global__ void __launch_bounds__(kBlockThreads) k_poisson(VecIn pin, const doub
   const int n = g.n, rows = g.rows, c = lg.cc;
   int r0, r1;
   if (!strip_rows(g, r0, r1)) return;
-  if (MODE != 3) halo_wait(pin, r0 == 0, r1 == rows);
+  if (MODE != 3 && (r0 == 0 || r1 == rows)) {
+    halo_fetch<true>(pin, 0, 1, 1, n, c, r0 == 0, r1 == rows);
+  }
   PushCtx pc{};
   if (PUSH) pc = push_begin(po, r0 == 0, r1 == rows);
   double th_m = th_row(th, r0 - 1, n)[c];
@@ -470,8 +433,8 @@ __global__ void __launch_bounds__(kBlockThreads) k_poisson(VecIn pin, const doub
         y[off] = out;
       }
       if (PUSH) {
-        if (r == 0) pc.prev[c] = out;
-        if (r == rows - 1) pc.next[c] = out;
+        if (r == 0) st_ll(pc.prev + c, out, pc.seq);
+        if (r == rows - 1) st_ll(pc.next + c, out, pc.seq);
       }
     }
     th_m = th_c; th_c = th_p; p_m = p_c; p_c = p_p; wv_c = wv_p; Hy_c = Hy_p;
@@ -488,7 +451,9 @@ __global__ void __launch_bounds__(kBlockThreads) k_div(VecIn win, const double* 
   const int n = g.n, rows = g.rows, c = lg.cc;
   int r0, r1;
   if (!strip_rows(g, r0, r1)) return;
-  halo_wait(win, r0 == 0, r1 == rows);
+  if (r0 == 0 || r1 == rows) {
+    halo_fetch<true>(win, 0, 4, 1, n, c, r0 == 0, r1 == rows);
+  }
   double th_m = th_row(th, r0 - 1, n)[c];
   double th_c = th_row(th, r0, n)[c];
   double vn_c = row_ptr(win, 1, r0, rows, n)[c], vs_c = row_ptr(win, 3, r0, rows, n)[c];
@@ -521,7 +486,9 @@ __global__ void __launch_bounds__(kBlockThreads) k_grad(VecIn pin, const double*
   const int n = g.n, rows = g.rows, c = lg.cc;
   int r0, r1;
   if (!strip_rows(g, r0, r1)) return;
-  halo_wait(pin, r0 == 0, r1 == rows);
+  if (r0 == 0 || r1 == rows) {
+    halo_fetch<true>(pin, 0, 1, 1, n, c, r0 == 0, r1 == rows);
+  }
   PushCtx pc{};
   if (PUSH) pc = push_begin(po, r0 == 0, r1 == rows);
   double th_m = th_row(th, r0 - 1, n)[c];
@@ -542,8 +509,14 @@ __global__ void __launch_bounds__(kBlockThreads) k_grad(VecIn pin, const double*
       y[off + 2 * fs] = g2;
       y[off + 3 * fs] = g3;
       if (PUSH) {
-        if (r == 0) { pc.prev[c] = g0; pc.prev[n + c] = g1; pc.prev[2 * n + c] = g2; pc.prev[3 * n + c] = g3; }
-        if (r == rows - 1) { pc.next[c] = g0; pc.next[n + c] = g1; pc.next[2 * n + c] = g2; pc.next[3 * n + c] = g3; }
+        if (r == 0) {
+          st_ll(pc.prev + c, g0, pc.seq); st_ll(pc.prev + n + c, g1, pc.seq);
+          st_ll(pc.prev + 2 * n + c, g2, pc.seq); st_ll(pc.prev + 3 * n + c, g3, pc.seq);
+        }
+        if (r == rows - 1) {
+          st_ll(pc.next + c, g0, pc.seq); st_ll(pc.next + n + c, g1, pc.seq);
+          st_ll(pc.next + 2 * n + c, g2, pc.seq); st_ll(pc.next + 3 * n + c, g3, pc.seq);
+        }
       }
     }
     th_m = th_c; p_m = p_c;
@@ -560,7 +533,11 @@ __global__ void k_restrict_F(VecIn fin, double* __restrict__ yc, int nf, int row
   const int nc = nf >> 1, rows_c = rows_f >> 1;
   const int C = blockIdx.x * blockDim.x + threadIdx.x;
   const int R = blockIdx.y;
-  halo_wait(fin, R == 0, R == (rows_f >> 1) - 1);
+  if (R == 0 && C < nc) {
+    // only the v-type fields of fine row -1 are read (columns 2C, 2C+1)
+    halo_fetch(fin, 1, 2, 2, nf, 2 * C, true, false);
+    halo_fetch(fin, 1, 2, 2, nf, 2 * C + 1, true, false);
+  }
   PushCtx pc{};
   if (PUSH) pc = push_begin(po, R == 0, R == rows_c - 1);
   if (C < nc && R < rows_c) {
@@ -581,8 +558,8 @@ __global__ void k_restrict_F(VecIn fin, double* __restrict__ yc, int nf, int row
     const double cv = 0.25 * wm + 0.5 * w0 + 0.25 * wp;
     yc[(2 * ph + 1) * fsc + (size_t)R * nc + C] = cv;
     if (PUSH) {
-      if (R == 0) { pc.prev[(2 * ph) * nc + C] = cu; pc.prev[(2 * ph + 1) * nc + C] = cv; }
-      if (R == rows_c - 1) { pc.next[(2 * ph) * nc + C] = cu; pc.next[(2 * ph + 1) * nc + C] = cv; }
+      if (R == 0) { st_ll(pc.prev + (2 * ph) * nc + C, cu, pc.seq); st_ll(pc.prev + (2 * ph + 1) * nc + C, cv, pc.seq); }
+      if (R == rows_c - 1) { st_ll(pc.next + (2 * ph) * nc + C, cu, pc.seq); st_ll(pc.next + (2 * ph + 1) * nc + C, cv, pc.seq); }
     }
   }
   }
@@ -594,11 +571,14 @@ __global__ void k_prolong_add_F(VecIn cin, double* __restrict__ xf, int nf, int 
   const int nc = nf >> 1, rows_c = rows_f >> 1;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;
-  halo_wait(cin, r == 0, r == rows_f - 1);
   if (c >= nf || r >= rows_f) return;
   const size_t fsf = (size_t)rows_f * nf;
   const int C = c >> 1, R = r >> 1;
   const int Cp = (C + 1 == nc) ? 0 : C + 1;
+  if (r == rows_f - 1) {
+    // only the v-type fields of coarse row rows_c are read (column C)
+    halo_fetch(cin, 1, 2, 2, nc, C, false, true);
+  }
 #pragma unroll
   for (int ph = 0; ph < 2; ++ph) {
     const double* uc = row_ptr(cin, 2 * ph, R, rows_c, nc);
@@ -635,8 +615,8 @@ __global__ void k_prolong_add_P(const double* __restrict__ xc, double* __restric
     const double v = xf[(size_t)r * nf + c] + xc[(size_t)(r >> 1) * nc + (c >> 1)];
     xf[(size_t)r * nf + c] = v;
     if (PUSH) {
-      if (r == 0) pc.prev[c] = v;
-      if (r == rows_f - 1) pc.next[c] = v;
+      if (r == 0) st_ll(pc.prev + c, v, pc.seq);
+      if (r == rows_f - 1) st_ll(pc.next + c, v, pc.seq);
     }
   }
   if (PUSH) push_end(po, pc, r == 0, r == rows_f - 1, gridDim.x, gridDim.x, gridDim.y == 1);

@@ -36,9 +36,8 @@ struct StokesArgs {
   ChebEp ce;                 // EP 1
   double* bc;                // EP 2: coarse rhs, field stride rows_c*nc
   PushOut po;                // PUSH
-  double* stash;             // distributed levels: edge strips copy the halo rows they received to this static
-                             // [2][5][n] buffer, so a later kernel (prolongation + sweep) can read them again
-                             // after newer exchanges have recycled the comm slots
+  // (distributed levels: xin.land may point at a static per-level stash instead of the transient landing buffer, so a
+  // later kernel -- prolongation + sweep -- can read the received rows again after newer exchanges recycled the slots)
 };
 
 template <int EP>
@@ -67,23 +66,24 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
   const Phys& ph = a.ph;
   VecIn xin = a.xin;
   VecIn cin = a.cin;
-  if (EDGE) {
-    halo_wait(xin, r0 == 0, r1 == rows);
-    if (IN == 2) halo_wait(cin, r0 == 0, r1 == rows);
-    if (a.stash != nullptr && xin.dseq != nullptr && lane >= LOFF && lane < LOFF + WC && j < n) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (r0 == 0) a.stash[k * n + c] = xin.top[k * xin.hs + c];
-        if (r1 == rows) a.stash[(5 + k) * n + c] = xin.bot[k * xin.hs + c];
-      }
+  if (EDGE && (r0 == 0 || r1 == rows)) {
+    // every lane fetches the halo elements of its own column (the only ones it reads) and lands them
+    if (xin.dseq != nullptr) {
+      halo_fetch<true>(xin, 0, WITH_P ? 5 : 4, 1, n, c, r0 == 0, r1 == rows);
+    }
+    if (IN == 2 && cin.dseq != nullptr) {
+      const int ncc = a.nc, Cc = c >> 1, Cq = (Cc + 1 == ncc) ? 0 : Cc + 1;
+      halo_fetch<true>(cin, 0, 4, 1, ncc, Cc, r0 == 0, r1 == rows);
+      halo_fetch<true>(cin, 0, 4, 1, ncc, Cq, r0 == 0, r1 == rows);
     }
   }
 
   // PUSH: my first / last output rows also go to the ring neighbours' halo areas (peer memory over NVLink)
   PushCtx pc{};
   if (PUSH) pc = push_begin(a.po, EDGE && r0 == 0, EDGE && r1 == rows);
-  double* const push_prev = pc.prev;
-  double* const push_next = pc.next;
+  LLElem* const push_prev = pc.prev;
+  LLElem* const push_next = pc.next;
+  const unsigned long long push_seq = pc.seq;
 
   const size_t fs = xin.fs;
   const double* __restrict__ th = a.th;
@@ -355,18 +355,18 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
         tv_s_m1 = tvs;
       }
     }
-    if (PUSH && store && live) {
+    if (PUSH && EDGE && store && live) {
       if (r == 0) {
-        push_prev[c] = y_un;
-        push_prev[n + c] = y_vn;
-        push_prev[2 * n + c] = y_us;
-        push_prev[3 * n + c] = y_vs;
+        st_ll(push_prev + c, y_un, push_seq);
+        st_ll(push_prev + n + c, y_vn, push_seq);
+        st_ll(push_prev + 2 * n + c, y_us, push_seq);
+        st_ll(push_prev + 3 * n + c, y_vs, push_seq);
       }
       if (r == rows - 1) {
-        push_next[c] = y_un;
-        push_next[n + c] = y_vn;
-        push_next[2 * n + c] = y_us;
-        push_next[3 * n + c] = y_vs;
+        st_ll(push_next + c, y_un, push_seq);
+        st_ll(push_next + n + c, y_vn, push_seq);
+        st_ll(push_next + 2 * n + c, y_us, push_seq);
+        st_ll(push_next + 3 * n + c, y_vs, push_seq);
       }
     }
     // rotate the window

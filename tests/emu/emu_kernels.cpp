@@ -236,11 +236,12 @@ void emu_slab_apply_A(int P, int rounds, int n, const double* prm, const double*
                       int rs) {
   const int rows = n / P;
   const size_t fs = (size_t)rows * n, area = (size_t)5 * n;
-  const size_t comm_bytes = kFlagBytes + 4 * area * sizeof(double);
+  const size_t comm_bytes = comm_halo_bytes(area);
   std::vector<std::vector<char>> comm(P, std::vector<char>(comm_bytes, 0));
   std::vector<unsigned long long> dseq(P, 0ull);
   std::vector<unsigned int> counter(P, 0u);
   std::vector<std::vector<double>> xs(P, std::vector<double>(5 * fs)), ys(P, std::vector<double>(5 * fs)), thp(P);
+  std::vector<std::vector<double>> land(P, std::vector<double>(2 * 5 * n, 0.0));
   std::vector<Tables> tabs(P);
   for (int g = 0; g < P; ++g) {
     for (int k = 0; k < 5; ++k)
@@ -267,6 +268,7 @@ void emu_slab_apply_A(int P, int rounds, int n, const double* prm, const double*
       in.dseq = &dseq[g];
       in.comm = comm[g].data();
       in.area = area;
+      in.land = land[g].data(); in.top = in.land; in.bot = in.land + 5 * n;
       StokesArgs a{};
       a.xin = in; a.th = thp[g].data(); a.y = ys[g].data(); a.g = geo; a.ph = ph;
       emu::launch(dim3((n + kWarpCols * kBlockWarps - 1) / (kWarpCols * kBlockWarps), (rows + rs - 1) / rs),
@@ -285,12 +287,13 @@ void emu_slab_fused_push_chain(int P, int n, const double* prm, const double* th
                                double* out, int rs, double omega) {
   const int rows = n / P;
   const size_t fs = (size_t)rows * n, area = (size_t)5 * n;
-  const size_t comm_bytes = kFlagBytes + 4 * area * sizeof(double);
+  const size_t comm_bytes = comm_halo_bytes(area);
   std::vector<std::vector<char>> comm(P, std::vector<char>(comm_bytes, 0));
   std::vector<unsigned long long> dseq(P, 0ull);
   std::vector<std::vector<unsigned int>> counter(P, std::vector<unsigned int>(8, 0u));
   std::vector<std::vector<double>> xa(P, std::vector<double>(4 * fs)), xb(P, std::vector<double>(4 * fs)),
       bs(P, std::vector<double>(4 * fs)), thp(P);
+  std::vector<std::vector<double>> land(P, std::vector<double>(2 * 5 * n, 0.0));
   std::vector<Tables> tabs(P);
   for (int g = 0; g < P; ++g) {
     for (int k = 0; k < 4; ++k) {
@@ -310,6 +313,7 @@ void emu_slab_fused_push_chain(int P, int n, const double* prm, const double* th
     in.dseq = &dseq[g];
     in.comm = comm[g].data();
     in.area = area;
+    in.land = land[g].data(); in.top = in.land; in.bot = in.land + 5 * n;
     return in;
   };
   // exchange 1: classic push kernel of x0
@@ -355,7 +359,7 @@ void emu_slab_fused_vcycle_chain(int P, int n, const double* prm, const double* 
                                  const double* wd, const double* ec, double* out_x, double* out_r, int rs, double omega) {
   const int rows = n / P, nc = n / 2, rows_c = rows / 2;
   const size_t fs = (size_t)rows * n, fsc = (size_t)rows_c * nc, area = (size_t)5 * n;
-  const size_t comm_bytes = kFlagBytes + 4 * area * sizeof(double);
+  const size_t comm_bytes = comm_halo_bytes(area);
   std::vector<std::vector<char>> comm(P, std::vector<char>(comm_bytes, 0));
   std::vector<unsigned long long> dseq(P, 0ull);
   std::vector<std::vector<unsigned int>> counter(P, std::vector<unsigned int>(8, 0u));
@@ -367,6 +371,7 @@ void emu_slab_fused_vcycle_chain(int P, int n, const double* prm, const double* 
     return v;
   };
   std::vector<std::vector<double>> bs(P), ws(P), es(P), x2(P), rr(P), x3(P), x4(P), thp(P), wdh(P), stash(P);
+  std::vector<std::vector<double>> land(P, std::vector<double>(2 * 5 * n, 0.0));
   std::vector<Tables> tabs(P);
   for (int g = 0; g < P; ++g) {
     bs[g] = slab(b, n, rows, g);
@@ -388,6 +393,7 @@ void emu_slab_fused_vcycle_chain(int P, int n, const double* prm, const double* 
   auto live = [&](int g, const double* x, size_t f, int hs) {
     VecIn in{};
     in.x = x; in.fs = f; in.hs = hs; in.dseq = &dseq[g]; in.comm = comm[g].data(); in.area = area;
+    in.land = land[g].data(); in.top = in.land; in.bot = in.land + 5 * hs;  // landing buffer = the view's halo rows
     return in;
   };
   auto base = [&](int g) {
@@ -422,7 +428,8 @@ void emu_slab_fused_vcycle_chain(int P, int n, const double* prm, const double* 
     a.xin = live(g, x2[g].data(), fs, n);
     a.b = bs[g].data();
     a.y = rr[g].data();
-    a.stash = stash[g].data();
+    a.xin.land = stash[g].data();  // land x2's halo rows in the static stash instead
+    a.xin.top = a.xin.land; a.xin.bot = a.xin.land + 5 * n;
     emu::launch(grid, dim3(kBlockThreads), [&] { k_stokes_x<0, 1, false, 0, true, 0>(a); });
   }
   push(es, fsc, rows_c, nc);
