@@ -26,7 +26,7 @@ struct CoarseLevel {
 struct CoarseArgs {
   int nlev;  // levels of the sub-hierarchy; the last one is solved with the dense (pseudo-)inverse
   CoarseLevel lev[kCoarseMaxLevels];
-  const double* Minv_t;  // column-major dense inverse of the coarsest level
+  const double* Minv_t;  // row-major dense inverse of the coarsest level
   int m;
   const double* b_in;  // rhs on the first level of the sub-hierarchy
   double* x_out;       // result on the first level
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(IS_F ? kCoarseThreadsF : kCoarseThreadsP) k_co
     double* x = (last == 0) ? a.x_out : L.x;
     for (int i = threadIdx.x; i < a.m; i += blockDim.x) {
       double acc = 0.0;
-      for (int k = 0; k < a.m; ++k) acc = fma(a.Minv_t[(size_t)k * a.m + i], b[k], acc);
+      for (int k = 0; k < a.m; ++k) acc = fma(a.Minv_t[(size_t)i * a.m + k], b[k], acc);
       x[i] = acc;
     }
     __syncthreads();

@@ -11,12 +11,13 @@ struct alignas(16) LLElem {
   unsigned long long tag;
 };
 #ifdef MPBP_EMU
+// host emulation (tests/emu): value first, then the tag with release / acquire ordering
 __device__ __forceinline__ void st_ll(LLElem* p, double v, unsigned long long tag) {
   p->v = v;
-  *(volatile unsigned long long*)&p->tag = tag;
+  __atomic_store_n(&p->tag, tag, __ATOMIC_RELEASE);
 }
 __device__ __forceinline__ double ld_ll(const LLElem* p, unsigned long long& tag) {
-  tag = *(const volatile unsigned long long*)&p->tag;
+  tag = __atomic_load_n(&p->tag, __ATOMIC_ACQUIRE);
   return p->v;
 }
 #else

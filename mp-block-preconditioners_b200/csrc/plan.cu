@@ -93,7 +93,7 @@ struct mpbp_plan {
   ncclComm_t comm = nullptr;
   std::vector<Level> lev;
   int first_repl = -1;  // index of the first replicated level when nranks > 1 (else -1)
-  // coarsest dense (pseudo-)inverses, column-major on the device
+  // coarsest dense (pseudo-)inverses, row-major on the device
   double *FinvT = nullptr, *PinvT = nullptr;
   int mF = 0, mP = 0;
   // tables for the analytic mass term (level 0)
@@ -403,7 +403,7 @@ static int launch_sx(mpbp_plan* p, int l, SxKind k, StokesArgs& a) {
   a.g = (k.in == 2) ? v.geo4 : v.geo;
   a.ph = v.ph;
   const int wc = (k.ep == 2) ? WarpTile<2>::cols : WarpTile<0>::cols;
-  if ((k.in == 2 || k.ep == 2) && ((v.rows & 1) || (a.g.rs & 1) || (a.g.re & 1) || (v.dist && k.ep == 2)))
+  if ((k.in == 2 || k.ep == 2) && ((v.rows & 1) || (a.g.rs & 1) || (a.g.re & 1) || (v.dist && k.ep == 2 && !k.push)))
     return set_err(MPBP_E_STATE, "internal: row-pair kernel on an odd / distributed level (rows %d, rs %d)", v.rows, a.g.rs);
   const dim3 grid((unsigned)((v.n + wc * kBlockWarps - 1) / (wc * kBlockWarps)), (unsigned)strip_count(a.g));
   if (k.push) a.po = push_out(p);
@@ -420,6 +420,7 @@ static int launch_sx(mpbp_plan* p, int l, SxKind k, StokesArgs& a) {
     case 12000: sx_launch<1, 2, false, 0, false, 5>(p, grid, a); break;  // pre-smoothing pair from b
     case 12001: sx_launch<1, 2, false, 0, true, 5>(p, grid, a); break;
     case 1020: sx_launch<0, 1, false, 2, false, 5>(p, grid, a); break;   // residual + restriction
+    case 1021: sx_launch<0, 1, false, 2, true, 5>(p, grid, a); break;    // ... on a slab of a distributed level
     case 22000: sx_launch<2, 2, false, 0, false, 4>(p, grid, a); break;  // prolongation + first post-sweep
     case 22001: sx_launch<2, 2, false, 0, true, 4>(p, grid, a); break;
     case 22010: sx_launch<2, 2, false, 1, false, 4>(p, grid, a); break;  // ... which is also the last one
@@ -483,20 +484,33 @@ static int op_presmooth_pair(mpbp_plan* p, int l, const double* b, double* y) {
   if (k.push) p->pending_push = y;
   return 0;
 }
-// coarse rhs b_{l+1} = R (b - F x): residual and full-weighting restriction in one pass (whole-grid levels)
-static int op_residual_restrict(mpbp_plan* p, int l, const double* x, const double* b) {
+// coarse rhs b_{l+1} = R (b - F x): residual and full-weighting restriction in one pass.  On a distributed level the
+// kernel also exchanges what the restriction needs across the slab boundary (the previous rank's last-row half-sums),
+// pushes the coarse rhs's own boundary rows to the ring neighbours (it is the next level's pre-smoother input) and
+// lands x's halo rows in the level's stash for the prolongation + sweep kernel of the same cycle.
+static int op_residual_restrict(mpbp_plan* p, int l, const double* x, const double* b, bool stash) {
   Level& v = p->lev[l];
   Level& c = p->lev[l + 1];
+  const bool gather = v.dist && (l + 1 == p->first_repl);
   StokesArgs a{};
-  RET(make_view(p, v, x, 4, a.xin));
+  RET(make_view(p, v, x, 4, a.xin, stash));
   a.b = b;
-  a.bc = c.bF;
+  a.bc = gather ? c.gF : c.bF;
   a.nc = c.n;
-  a.rows_c = c.rows;
+  a.rows_c = v.rows / 2;
   SxKind k;
   k.mode = 1;
   k.ep = 2;
-  return launch_sx(p, l, k, a);
+  k.push = v.dist;
+  RET(launch_sx(p, l, k, a));
+  if (k.push && c.dist) p->pending_push = c.bF;
+  if (gather) {
+    const size_t cnt = (size_t)(v.rows / 2) * c.n;
+    NC(ncclGroupStart());
+    for (int f = 0; f < 4; ++f) NC(ncclAllGather(c.gF + f * cnt, c.bF + f * c.fs(), cnt, ncclDouble, p->comm, p->st));
+    NC(ncclGroupEnd());
+  }
+  return 0;
 }
 // y = xt + omega (b - F xt)/diag, xt = x + P x_{l+1}: coarse-grid correction + first post-smoothing sweep in one pass
 static int op_prolong_sweep(mpbp_plan* p, int l, const double* x, const double* b, double* y, double omega,
@@ -602,8 +616,8 @@ static int op_grad(mpbp_plan* p, int l, const double* pr, double* y) {
   if (push) p->pending_push = y;
   return 0;
 }
-static int op_dense(mpbp_plan* p, const double* Mt, const double* x, double* y, int m) {
-  k_dense_matvec<<<1, 256, m * sizeof(double), p->st>>>(Mt, x, y, m);
+static int op_dense(mpbp_plan* p, const double* M, const double* x, double* y, int m) {
+  k_dense_matvec<<<(m * 32 + 255) / 256, 256, 0, p->st>>>(M, x, y, m);
   LAUNCH_CHECK(p);
   return 0;
 }
@@ -923,7 +937,8 @@ static int vcycle(mpbp_plan* p, int l, bool isF, const double* b, double* x, con
   const bool even = !(v.rows & 1) && !(v.geo.rs & 1) && !(v.geo4.rs & 1);
   const bool dist_ok = !v.dist || (p->p2p && p->push_fused);  // distributed levels: fused variants need the peer-memory halos
   const bool fuse_pre = isF && (p->fuse & 1) && dist_ok && c.nu1 == 2 && v.wdF != nullptr;
-  const bool fuse_rr = isF && (p->fuse & 4) && !v.dist && even;                  // residual + restriction
+  // residual + restriction (slabs: peer-memory halos and at least two coarse rows per rank)
+  const bool fuse_rr = isF && (p->fuse & 4) && even && (!v.dist || (dist_ok && v.rows >= 4));
   const bool fuse_post = isF && (p->fuse & 2) && dist_ok && even && c.nu2 >= 1;  // prolongation + first post-sweep
   // number of kernels that write the iterate into a fresh buffer (they ping-pong between x and t); the last one
   // must land in x unless it ends in the epilogue
@@ -947,7 +962,7 @@ static int vcycle(mpbp_plan* p, int l, bool isF, const double* b, double* x, con
   }
   // ---- coarse-grid correction ----
   if (fuse_rr) {
-    RET(op_residual_restrict(p, l, cur, b));
+    RET(op_residual_restrict(p, l, cur, b, /*stash=*/fuse_post));
   } else {
     if (isF) RET(op_stokes(p, l, 1, false, cur, b, r, 0.0, nullptr, /*stash=*/fuse_post));
     else RET(op_poisson(p, l, 1, cur, b, r, 0.0));
@@ -1135,7 +1150,7 @@ static int check_cfg(const mpbp_config* c) {
   if (c->n < 2) return set_err(MPBP_E_ARG, "n must be >= 2 (got %d)", c->n);
   if (c->nranks < 1 || c->rank < 0 || c->rank >= c->nranks) return set_err(MPBP_E_ARG, "bad rank/nranks");
   if (c->nranks > 1 && !c->nccl_unique_id) return set_err(MPBP_E_ARG, "nranks>1 needs nccl_unique_id");
-  if (c->n_coarse < 2 || c->n_coarse > 8) return set_err(MPBP_E_ARG, "n_coarse must be in [2,8]");
+  if (c->n_coarse < 2 || c->n_coarse > 16) return set_err(MPBP_E_ARG, "n_coarse must be in [2,16]");
   if (!(c->omega > 0.0)) return set_err(MPBP_E_ARG, "omega must be > 0");
   if (c->cheb && !(c->lmax > c->lmin && c->lmin > 0.0)) return set_err(MPBP_E_ARG, "need 0 < lmin < lmax");
   return 0;
@@ -1183,10 +1198,12 @@ static bool invert_dense(std::vector<double>& A, int m) {
       if (r == col) continue;
       const double f = A[(size_t)r * m + col];
       if (f == 0.0) continue;
-      for (int k = 0; k < m; ++k) {
-        A[(size_t)r * m + k] -= f * A[(size_t)col * m + k];
-        I[(size_t)r * m + k] -= f * I[(size_t)col * m + k];
-      }
+      double* __restrict__ Ar = &A[(size_t)r * m];
+      double* __restrict__ Ir = &I[(size_t)r * m];
+      const double* __restrict__ Ac = &A[(size_t)col * m];
+      const double* __restrict__ Ic = &I[(size_t)col * m];
+      for (int k = col; k < m; ++k) Ar[k] -= f * Ac[k];  // columns < col of the pivot row are already zero
+      for (int k = 0; k < m; ++k) Ir[k] -= f * Ic[k];
     }
   }
   A.swap(I);
@@ -1223,11 +1240,7 @@ static int build_coarse_inverses(mpbp_plan* p) {
     } else if (!invert_dense(M, m)) {
       return set_err(MPBP_E_STATE, "coarse F is singular");
     }
-    // column-major upload: Mt[k*m+i] = M[i][k]
-    std::vector<double> Mt((size_t)m * m);
-    for (int i = 0; i < m; ++i)
-      for (int k = 0; k < m; ++k) Mt[(size_t)k * m + i] = M[(size_t)i * m + k];
-    CU(cudaMemcpyAsync(isF ? p->FinvT : p->PinvT, Mt.data(), Mt.size() * sizeof(double), cudaMemcpyHostToDevice, p->st));
+    CU(cudaMemcpyAsync(isF ? p->FinvT : p->PinvT, M.data(), M.size() * sizeof(double), cudaMemcpyHostToDevice, p->st));
     CU(cudaStreamSynchronize(p->st));
   }
   return 0;

@@ -623,17 +623,27 @@ __global__ void k_prolong_add_P(const double* __restrict__ xc, double* __restric
 }
 
 #ifndef MPBP_EMU
-// y = M x for the coarsest-level dense (pseudo-)inverse; Mt is column-major (Mt[k*m+i] = M[i][k])
-__global__ void k_dense_matvec(const double* __restrict__ Mt, const double* __restrict__ x, double* __restrict__ y,
-                               int m) {
-  extern __shared__ double sx[];
-  for (int i = threadIdx.x; i < m; i += blockDim.x) sx[i] = x[i];
-  __syncthreads();
-  for (int i = threadIdx.x; i < m; i += blockDim.x) {
-    double acc = 0.0;
-    for (int k = 0; k < m; ++k) acc = fma(Mt[(size_t)k * m + i], sx[k], acc);
-    y[i] = acc;
+// y = M x for the coarsest-level dense (pseudo-)inverse, M row-major: one warp per row (coalesced row read, fixed
+// summation order), m/8 blocks -- at n_coarse = 16 (m = 1024, 8 MB, L2-resident) one launch of a few microseconds
+// replaces three multigrid levels of latency-bound kernels
+__global__ void __launch_bounds__(256) k_dense_matvec(const double* __restrict__ M, const double* __restrict__ x,
+                                                      double* __restrict__ y, int m) {
+  const int row = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= m) return;
+  const double* __restrict__ mr = M + (size_t)row * m;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int k = lane;
+  for (; k + 96 < m; k += 128) {
+    a0 = fma(mr[k], x[k], a0);
+    a1 = fma(mr[k + 32], x[k + 32], a1);
+    a2 = fma(mr[k + 64], x[k + 64], a2);
+    a3 = fma(mr[k + 96], x[k + 96], a3);
   }
+  for (; k < m; k += 32) a0 = fma(mr[k], x[k], a0);
+  double acc = (a0 + a1) + (a2 + a3);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+  if (lane == 0) y[row] = acc;
 }
 #endif  // MPBP_EMU
 

@@ -55,6 +55,10 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
   static_assert(!(EP == 1 && MODE != 2), "Chebyshev epilogue belongs to the last sweep");
   static_assert(!(WITH_P && (IN != 0 || EP != 0 || MODE != 0)), "the pressure coupling is only used by y = A x");
   constexpr int WC = WarpTile<EP>::cols, LOFF = WarpTile<EP>::loff;
+  // EP 2 on whole-grid levels addresses rows periodically in place (it reaches row r0-2); with PUSH the level is a
+  // slab of a distributed grid: rows -1 / `rows` are halo rows and the slab's first coarse row is finished with the
+  // previous rank's contribution (see the end of this function)
+  constexpr bool WRAP = (EP == 2) && !PUSH;
   const int n = a.g.n, rows = a.g.rows;
   const int lane = threadIdx.x & 31;
   const int j0 = (blockIdx.x * kBlockWarps + (threadIdx.x >> 5)) * WC;
@@ -95,7 +99,7 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
   const bool codd = (c & 1) != 0;
   auto wrap_row = [&](int rr) -> int { return rr < 0 ? rr + rows : (rr >= rows ? rr - rows : rr); };
   auto xrow = [&](const VecIn& v, int k, int rr) -> const double* {
-    if (EP == 2) return v.x + k * v.fs + (size_t)wrap_row(rr) * n;  // whole-grid levels only: periodic in place
+    if (WRAP) return v.x + k * v.fs + (size_t)wrap_row(rr) * n;  // whole-grid levels only: periodic in place
     return row_ptr(v, k, rr, rows, n);
   };
   const int fs32 = (int)fs;  // 4 fields of one slab stay below 2^31 elements (checked at plan creation)
@@ -161,7 +165,9 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
   }
 
   // EP 2 starts one row early (stores off): the v-type restriction of coarse row r0/2 needs the residual of row r0-1
-  int r = (EP == 2) ? r0 - 1 : r0;
+  // (a slab's first strip cannot: row -1 belongs to the previous rank, which sends its half-sums instead)
+  const bool pre_step = (EP == 2) && !(PUSH && r0 == 0);
+  int r = pre_step ? r0 - 1 : r0;
 
   // ---- prologue: rows r-1 and r (r is even whenever row parity matters: IN 2 / EP 2 start strips on even rows,
   //      EP 2 then steps back to the odd row r0-1) ----
@@ -171,8 +177,8 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
     if (IN == 2) v += pe(k, rr, odd_row);
     return v;
   };
-  double th_m = th_row(th, (EDGE && EP == 2) ? wrap_row(r - 1) : r - 1, n)[c];
-  double th_c = th_row(th, (EDGE && EP == 2) ? wrap_row(r) : r, n)[c];
+  double th_m = th_row(th, (EDGE && WRAP) ? wrap_row(r - 1) : r - 1, n)[c];
+  double th_c = th_row(th, (EDGE && WRAP) ? wrap_row(r) : r, n)[c];
   double un_m = ldx(0, r - 1, !r_odd), vn_m = ldx(1, r - 1, !r_odd), us_m = ldx(2, r - 1, !r_odd), vs_m = ldx(3, r - 1, !r_odd);
   double un_c = ldx(0, r, r_odd), vn_c = ldx(1, r, r_odd), us_c = ldx(2, r, r_odd), vs_c = ldx(3, r, r_odd);
   double p_m = 0.0, p_c = 0.0;
@@ -191,7 +197,7 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
   double Vsum_c = vs_c + fv_c * (vn_c - vs_c);
 
   // next row (r+1) raw values, loaded one row ahead of use
-  double th_p = th_row(th, (EDGE && EP == 2) ? wrap_row(r + 1) : r + 1, n)[c];
+  double th_p = th_row(th, (EDGE && WRAP) ? wrap_row(r + 1) : r + 1, n)[c];
   double un_p = ldx(0, r + 1, !r_odd), vn_p = ldx(1, r + 1, !r_odd), us_p = ldx(2, r + 1, !r_odd), vs_p = ldx(3, r + 1, !r_odd);
   double p_p = 0.0;
   if (WITH_P) p_p = EDGE ? row_ptr(xin, 4, r + 1, rows, n)[c] : xin.x[(r + 1) * n + c + 4 * fs32];
@@ -200,12 +206,13 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
   double ru_n_prev = 0.0, ru_s_prev = 0.0;          // u-type residual of the even row of the current pair
   double tv_n_m1 = 0.0, tv_s_m1 = 0.0;              // v-type column half-sum of row 2R-1
   double tv_n_0 = 0.0, tv_s_0 = 0.0;                // ... of row 2R
+  double dtv0_n = 0.0, dtv0_s = 0.0, dtvp_n = 0.0, dtvp_s = 0.0;  // slab: rows 0 / 1 half-sums of the deferred first coarse row
 
   // One marching step: produce output row r (parity known at compile time per call site), take in row r+2.
   auto step = [&](const bool odd_out, const bool live) {
     // incoming row r+2 (same parity as r), clamped to r1: the last one is unused but stays inside the halo
     const int rq = EDGE ? min(r + 2, r1) : r + 2;
-    const double th_q = th_row(th, (EDGE && EP == 2) ? wrap_row(rq) : rq, n)[c];
+    const double th_q = th_row(th, (EDGE && WRAP) ? wrap_row(rq) : rq, n)[c];
     const double un_q = ldx(0, rq, odd_out), vn_q = ldx(1, rq, odd_out);
     const double us_q = ldx(2, rq, odd_out), vs_q = ldx(3, rq, odd_out);
     double p_q = 0.0;
@@ -218,7 +225,7 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
     double bn_u = 0.0, bn_v = 0.0, bs_u = 0.0, bs_v = 0.0;
     if (MODE != 0) {
       const double* bb = (IN == 1) ? xin.x : b;  // IN 1: the rhs IS the streamed input
-      const int ob = (EDGE && EP == 2 && r < 0) ? wrap_row(r) * n + c : off;
+      const int ob = (EDGE && WRAP && r < 0) ? wrap_row(r) * n + c : off;
       bn_u = bb[ob];
       bn_v = bb[ob + fs32];
       bs_u = bb[ob + 2 * fs32];
@@ -239,7 +246,7 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
     const double fu_c = 0.5 * a_c;
     double mu, mv;
     if (ph.mass_mode) {
-      const int gr = a.g.row0 + ((EDGE && EP == 2) ? wrap_row(r) : r);
+      const int gr = a.g.row0 + ((EDGE && WRAP) ? wrap_row(r) : r);
       mu = 0.25 * sxf * ph.syc[gr] + 0.5;  // thn(-(r+1/2)h, c h), preconditioner.py:325
       mv = 0.25 * sxc * ph.syf[gr] + 0.5;  // thn(-r h, (c+1/2)h), preconditioner.py:326
     } else {
@@ -341,21 +348,44 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
         const double sun = 0.5 * (ru_n_prev + y_un), sus = 0.5 * (ru_s_prev + y_us);
         const double cu_n = 0.25 * shfl_up1(sun) + 0.5 * sun + 0.25 * shfl_dn1(sun);
         const double cu_s = 0.25 * shfl_up1(sus) + 0.5 * sus + 0.25 * shfl_dn1(sus);
+        // slab (PUSH): the v-type weights of the first coarse row need fine row -1, which the previous rank owns
+        const bool defer = PUSH && EDGE && r == 1;
         const double cv_n = 0.25 * tv_n_m1 + 0.5 * tv_n_0 + 0.25 * tvn;
         const double cv_s = 0.25 * tv_s_m1 + 0.5 * tv_s_0 + 0.25 * tvs;
+        if (defer) {
+          dtv0_n = tv_n_0; dtv0_s = tv_s_0; dtvp_n = tvn; dtvp_s = tvs;
+        }
         if (store && live && !codd) {
           double* __restrict__ bc = a.bc;
           const int oc = (r >> 1) * nc + C;
           bc[oc] = cu_n;
-          bc[oc + fsc32] = cv_n;
           bc[oc + 2 * fsc32] = cu_s;
-          bc[oc + 3 * fsc32] = cv_s;
+          if (!defer) {
+            bc[oc + fsc32] = cv_n;
+            bc[oc + 3 * fsc32] = cv_s;
+          }
+          if (PUSH && EDGE) {
+            // the coarse rhs is the next level's pre-smoother input: its first / last rows go to the ring neighbours
+            if (r == 1) {
+              st_ll(push_prev + C, cu_n, push_seq);
+              st_ll(push_prev + 2 * nc + C, cu_s, push_seq);
+            }
+            if (r == rows - 1) {
+              st_ll(push_next + C, cu_n, push_seq);
+              st_ll(push_next + nc + C, cv_n, push_seq);
+              st_ll(push_next + 2 * nc + C, cu_s, push_seq);
+              st_ll(push_next + 3 * nc + C, cv_s, push_seq);
+              // ... and this row's half-sums complete the next rank's first coarse row
+              st_ll(push_next + 4 * nc + C, tvn, push_seq);
+              st_ll(push_next + 5 * nc + C, tvs, push_seq);
+            }
+          }
         }
         tv_n_m1 = tvn;
         tv_s_m1 = tvs;
       }
     }
-    if (PUSH && EDGE && store && live) {
+    if (PUSH && EDGE && EP != 2 && store && live) {
       if (r == 0) {
         st_ll(push_prev + c, y_un, push_seq);
         st_ll(push_prev + n + c, y_vn, push_seq);
@@ -380,7 +410,7 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
     ++r;
   };
 
-  if (EP == 2) step(true, false);  // row r0-1 (odd): only its v-type half-sums are kept
+  if (pre_step) step(true, false);  // row r0-1 (odd): only its v-type half-sums are kept
   if (IN == 2 || EP == 2) {
     // row pairs: strips start on even rows and coarsened levels have even row counts
     while (r < r1) {
@@ -394,6 +424,19 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
     }
   }
 
+  if (EP == 2 && PUSH && EDGE && r0 == 0 && store && !codd) {
+    // first coarse row of the slab, v-type fields: the half-sums of fine row -1 arrive from the previous rank (its last
+    // strip sends them under this kernel's own exchange number; both edge strips run in the first wave on every rank)
+    const LLElem* mine = comm_halo(a.po.my_comm, a.po.area, (int)(push_seq % (unsigned long long)kHaloSlots), 0);
+    const double tm_n = ll_wait(mine + 4 * nc + C, push_seq);
+    const double tm_s = ll_wait(mine + 5 * nc + C, push_seq);
+    const double cv_n = 0.25 * tm_n + 0.5 * dtv0_n + 0.25 * dtvp_n;
+    const double cv_s = 0.25 * tm_s + 0.5 * dtv0_s + 0.25 * dtvp_s;
+    a.bc[C + fsc32] = cv_n;
+    a.bc[C + 3 * fsc32] = cv_s;
+    st_ll(push_prev + nc + C, cv_n, push_seq);
+    st_ll(push_prev + 3 * nc + C, cv_s, push_seq);
+  }
   if (PUSH) push_end(a.po, pc, r0 == 0, r1 == rows, gridDim.x, gridDim.x, gridDim.y == 1);
 }
 

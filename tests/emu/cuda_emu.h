@@ -93,32 +93,45 @@ inline ThreadState& ts() {
 }
 
 template <class F>
-void launch(dim3 grid, dim3 block, F body) {
+void run_block(dim3 grid, dim3 block, unsigned bx, unsigned by, F& body) {
   const int nthreads = (int)(block.x * block.y * block.z);
+  BlockCtx bc(nthreads);
+  const int nwarps = (nthreads + 31) / 32;
+  for (int w = 0; w < nwarps; ++w) bc.warps.push_back(new WarpCtx(std::min(32, nthreads - 32 * w)));
+  std::vector<std::thread> th;
+  th.reserve(nthreads);
+  for (int t = 0; t < nthreads; ++t) {
+    th.emplace_back([&, t]() {
+      ThreadState& s = ts();
+      s.tid = dim3((unsigned)t);
+      s.bid = dim3(bx, by);
+      s.bdim = block;
+      s.gdim = grid;
+      s.block = &bc;
+      s.warp = bc.warps[t / 32];
+      body();
+      s.warp->bar.drop();
+      s.block->bar.drop();
+    });
+  }
+  for (auto& x : th) x.join();
+  for (auto* w : bc.warps) delete w;
+}
+
+template <class F>
+void launch(dim3 grid, dim3 block, F body) {
   for (unsigned by = 0; by < grid.y; ++by)
-    for (unsigned bx = 0; bx < grid.x; ++bx) {
-      BlockCtx bc(nthreads);
-      const int nwarps = (nthreads + 31) / 32;
-      for (int w = 0; w < nwarps; ++w) bc.warps.push_back(new WarpCtx(std::min(32, nthreads - 32 * w)));
-      std::vector<std::thread> th;
-      th.reserve(nthreads);
-      for (int t = 0; t < nthreads; ++t) {
-        th.emplace_back([&, t]() {
-          ThreadState& s = ts();
-          s.tid = dim3((unsigned)t);
-          s.bid = dim3(bx, by);
-          s.bdim = block;
-          s.gdim = grid;
-          s.block = &bc;
-          s.warp = bc.warps[t / 32];
-          body();
-          s.warp->bar.drop();
-          s.block->bar.drop();
-        });
-      }
-      for (auto& x : th) x.join();
-      for (auto* w : bc.warps) delete w;
-    }
+    for (unsigned bx = 0; bx < grid.x; ++bx) run_block(grid, block, bx, by, body);
+}
+
+// All blocks of the launch run at the same time (one host thread per block): for kernels whose blocks wait for each
+// other or for another rank's blocks (small grids only; kernels with __shared__ statics cannot use it).
+template <class F>
+void launch_concurrent(dim3 grid, dim3 block, F body) {
+  std::vector<std::thread> blocks;
+  for (unsigned by = 0; by < grid.y; ++by)
+    for (unsigned bx = 0; bx < grid.x; ++bx) blocks.emplace_back([&, bx, by] { run_block(grid, block, bx, by, body); });
+  for (auto& b : blocks) b.join();
 }
 
 }  // namespace emu

@@ -11,6 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(HERE, "_build", "libmpbp_emu.so")
 SRCS = [os.path.join(HERE, "emu_kernels.cpp"), os.path.join(HERE, "cuda_emu.h"),
         os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "stencil.cuh"),
+        os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "ll.cuh"),
         os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "coarse.cuh"),
         os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "stokes.cuh")]
 _dp = C.POINTER(C.c_double)
@@ -104,7 +105,7 @@ def coarse_vcycle(isF, n, prm, mass_mode, theta, n_coarse, omega, nu1, nu2, Minv
     """Minv: row-major dense (pseudo-)inverse of the coarsest level."""
     b = np.ascontiguousarray(b, dtype=np.float64)
     x = np.zeros_like(b)
-    Mt = np.ascontiguousarray(Minv.T, dtype=np.float64)  # column-major storage of Minv == row-major of Minv^T
+    Mt = np.ascontiguousarray(Minv, dtype=np.float64)  # row-major, as plan.cu uploads it
     th = np.ascontiguousarray(theta, dtype=np.float64)
     load().emu_coarse_vcycle(int(isF), n, _p(prm), mass_mode, _p(th), n_coarse, C.c_double(omega), nu1, nu2, _p(Mt),
                              Minv.shape[0], _p(b), _p(x), threads)
@@ -160,3 +161,15 @@ def slab_fused_vcycle_chain(P, n, prm, theta, b, wd, ec, rs=4, omega=0.8):
     load().emu_slab_fused_vcycle_chain(P, n, _p(prm), _p(th), _p(b), _p(wd), _p(ec), _p(out_x), _p(out_r), rs,
                                        C.c_double(omega))
     return out_x, out_r
+
+
+def slab_residual_restrict(P, n, prm, theta, x, b, rs=4):
+    """EP 2 + PUSH: fused residual + restriction on P emulated slabs (ranks run concurrently).  Returns the assembled
+    coarse rhs and the coarse rows each rank received from its ring neighbours, [P][2 (top, bottom)][4][n/2]."""
+    c = lambda v: np.ascontiguousarray(v, dtype=np.float64)
+    x, b, th = c(x), c(b), c(theta)
+    nc = n // 2
+    out = np.zeros(4 * nc * nc)
+    rows = np.zeros((P, 2, 4, nc))
+    load().emu_slab_residual_restrict(P, n, _p(prm), _p(th), _p(x), _p(b), _p(out), _p(rows), rs)
+    return out, rows

@@ -456,4 +456,70 @@ void emu_slab_fused_vcycle_chain(int P, int n, const double* prm, const double* 
     }
 }
 
+// Fused residual + restriction on the slabs of a DISTRIBUTED level (EP 2 with PUSH), P ranks emulated: x's halo rows
+// are pushed first (all ranks), then every rank runs the kernel CONCURRENTLY (one host thread per rank): a slab's first
+// strip waits inside the kernel for the previous rank's last-row half-sums.  out_bc: assembled coarse rhs R (b - F x);
+// out_rows [P][2][4][nc]: the coarse rows each rank RECEIVED in its comm buffer (row -1 from the previous rank, row
+// rows_c from the next), i.e. what the next level's pre-smoother will read as halos.
+void emu_slab_residual_restrict(int P, int n, const double* prm, const double* theta, const double* x, const double* b,
+                                double* out_bc, double* out_rows, int rs) {
+  const int rows = n / P, nc = n / 2, rows_c = rows / 2;
+  const size_t fs = (size_t)rows * n, fsc = (size_t)rows_c * nc, area = (size_t)5 * n;
+  std::vector<std::vector<char>> comm(P, std::vector<char>(comm_halo_bytes(area), 0));
+  std::vector<unsigned long long> dseq(P, 0ull);
+  std::vector<std::vector<unsigned int>> counter(P, std::vector<unsigned int>(8, 0u));
+  std::vector<std::vector<double>> xs(P), bs(P), bc(P, std::vector<double>(4 * fsc, 0.0)), thp(P);
+  std::vector<std::vector<double>> land(P, std::vector<double>(2 * 5 * n, 0.0));
+  std::vector<Tables> tabs(P);
+  for (int g = 0; g < P; ++g) {
+    xs[g].resize(4 * fs);
+    bs[g].resize(4 * fs);
+    for (int k = 0; k < 4; ++k) {
+      std::memcpy(&xs[g][k * fs], x + (size_t)k * n * n + (size_t)g * rows * n, fs * sizeof(double));
+      std::memcpy(&bs[g][k * fs], b + (size_t)k * n * n + (size_t)g * rows * n, fs * sizeof(double));
+    }
+    thp[g].resize((size_t)(rows + 2) * n);
+    for (int r = -1; r <= rows; ++r)
+      std::memcpy(&thp[g][(size_t)(r + 1) * n], theta + (size_t)(((g * rows + r) % n + n) % n) * n, n * sizeof(double));
+  }
+  for (int g = 0; g < P; ++g) {
+    const int prev = (g + P - 1) % P, next = (g + 1) % P;
+    emu::launch(dim3((4 * n + 255) / 256), dim3(256), [&] {
+      k_halo_push(xs[g].data(), 4, fs, rows, n, comm[prev].data(), comm[next].data(), comm[g].data(), area, &dseq[g],
+                  &counter[g][0]);
+    });
+  }
+  std::vector<std::thread> ranks;
+  std::vector<StokesArgs> args(P);
+  for (int g = 0; g < P; ++g) {
+    const int prev = (g + P - 1) % P, next = (g + 1) % P;
+    StokesArgs& a = args[g];
+    a = StokesArgs{};
+    a.th = thp[g].data();
+    a.ph = make_phys(n, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], prm[6], 1, tabs[g]);
+    a.g = Geo{n, rows, g * rows, rs, 3};
+    a.xin.x = xs[g].data(); a.xin.fs = fs; a.xin.hs = n; a.xin.dseq = &dseq[g]; a.xin.comm = comm[g].data();
+    a.xin.area = area; a.xin.land = land[g].data(); a.xin.top = a.xin.land; a.xin.bot = a.xin.land + 5 * n;
+    a.b = bs[g].data();
+    a.bc = bc[g].data();
+    a.nc = nc;
+    a.rows_c = rows_c;
+    a.po = PushOut{comm[prev].data(), comm[next].data(), comm[g].data(), area, &dseq[g], &counter[g][4]};
+  }
+  const dim3 grid((n + WarpTile<2>::cols * kBlockWarps - 1) / (WarpTile<2>::cols * kBlockWarps), (rows + rs - 1) / rs);
+  for (int g = 0; g < P; ++g)
+    ranks.emplace_back([&, g] { emu::launch_concurrent(grid, dim3(kBlockThreads), [&, g] { k_stokes_x<0, 1, false, 2, true, 0>(args[g]); }); });
+  for (auto& t : ranks) t.join();
+  for (int g = 0; g < P; ++g) {
+    for (int k = 0; k < 4; ++k)
+      std::memcpy(out_bc + (size_t)k * nc * nc + (size_t)g * rows_c * nc, &bc[g][k * fsc], fsc * sizeof(double));
+    const int slot = (int)(dseq[g] % (unsigned long long)kHaloSlots);
+    for (int dir = 0; dir < 2; ++dir) {
+      const LLElem* e = comm_halo(comm[g].data(), area, slot, dir);
+      for (int i = 0; i < 4 * nc; ++i)
+        out_rows[((size_t)g * 2 + dir) * 4 * nc + i] = (e[i].tag == dseq[g]) ? e[i].v : std::nan("");
+    }
+  }
+}
+
 }  // extern "C"

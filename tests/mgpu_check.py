@@ -83,12 +83,19 @@ def main():
 
     def krylov_pair(tag, eta, A1_, M1_, Ad_, Md_, b1_, bd_, sides):
         # conditioning of the history: the same single-GPU solve with other (still deterministic) summation orders in
-        # the dot products -- the only arithmetic difference a slab run introduces.  Envelope over four of them.
+        # the dot products -- the only arithmetic difference a slab run introduces.  Envelope over eight of them.
+        # A slab run also changes WHICH code body computes a row (the first / last strip of a slab runs the general
+        # instantiation of the marching kernels, whose fused multiply-adds are contracted differently: V-cycles differ
+        # by an ulp), so two of the variants also use other strip heights.
         variants = []
-        for rb in ("211", "307", "401", "593"):
+        for rb, rs in (("211", None), ("307", "6"), ("401", "10"), ("593", None), ("149", "14"), ("257", None),
+                       ("449", "22"), ("1009", "8")):
             os.environ["MPBP_RED_BLOCKS"] = rb
+            if rs:
+                os.environ["MPBP_RS"] = rs
             bps = mp.MultiphaseBlockPreconditioner(n, xi, eta, eta_s, sub_solver=sub)
             variants.append((bps.get_big_A_matrix(c, d)[0], bps.approx_schur_operator(c, d)))
+            os.environ.pop("MPBP_RS", None)
         del os.environ["MPBP_RED_BLOCKS"]
         for side, name in sides:
             mi = 60 if side == SIDE_RIGHT else 5

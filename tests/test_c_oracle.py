@@ -26,20 +26,22 @@ def test_c_oracle_operators_vs_reference_golden(fx):
     assert relerr(co.apply_A(g["u_vec"]), g["Au"]) < 1e-13
 
 
-@pytest.mark.parametrize("n,eta_n,cheb", [(16, 100.0, True), (32, 1.0, False), (48, 1e3, True), (64, 1e4, True)])
-def test_c_oracle_subsolvers_and_preconditioner_vs_numpy_oracle(n, eta_n, cheb):
+@pytest.mark.parametrize("n,eta_n,cheb,n_coarse", [(16, 100.0, True, 4), (32, 1.0, False, 4), (48, 1e3, True, 4),
+                                                   (64, 1e4, True, 4), (64, 1e4, True, 16)])
+def test_c_oracle_subsolvers_and_preconditioner_vs_numpy_oracle(n, eta_n, cheb, n_coarse):
+    """n_coarse = 16 is the benchmarked hierarchy (bench.py: dense solve on the 16x16 grid)."""
     xi, eta_s, c, d = 1.0, 1.0, 1.0, -1.0
     ops = O.Operators(n, xi, eta_n, eta_s, c, d)
-    cfgF = O.SubSolverConfig(kind="mg", cycles=3, cheb=cheb)
-    cfgP = O.SubSolverConfig(kind="mg", cycles=2, cheb=cheb)
+    cfgF = O.SubSolverConfig(kind="mg", cycles=3, cheb=cheb, n_coarse=n_coarse)
+    cfgP = O.SubSolverConfig(kind="mg", cycles=2, cheb=cheb, n_coarse=n_coarse)
     Mo = O.ApproxSchur(ops, cfgF)
     Mo.P_inv = O.SubSolver(ops, "P", cfgP, O.Multigrid(ops, cfgP))
-    co = COracle(n, xi, eta_n, eta_s, c, d, F_cycles=3, P_cycles=2, cheb=cheb)
+    co = COracle(n, xi, eta_n, eta_s, c, d, F_cycles=3, P_cycles=2, cheb=cheb, n_coarse=n_coarse)
     rng = np.random.default_rng(n)
     N = n * n
     v = rng.standard_normal(5 * N)
     v[4 * N:] -= v[4 * N:].mean()
-    mg1 = O.Multigrid(ops, O.SubSolverConfig(kind="mg", cycles=1))
+    mg1 = O.Multigrid(ops, O.SubSolverConfig(kind="mg", cycles=1, n_coarse=n_coarse))
     # the coarsest 4x4 velocity block has condition number ~ 260 * eta_n/eta_s: two correct dense inverses
     # (Gauss-Jordan here, LAPACK in numpy) differ by eps * cond, which bounds the agreement of the F solves
     tolF = max(1e-10, 2e-13 * eta_n)

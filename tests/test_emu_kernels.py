@@ -202,3 +202,23 @@ def test_fused_vcycle_kernels_on_distributed_levels(P, n, rs):
     got_x, got_r = emu.slab_fused_vcycle_chain(P, n, prm, theta, b, wd, ec, rs=rs)
     assert relerr(got_r, b - ops.F @ x2) < 1e-12
     assert relerr(got_x, sweep(sweep(xt))) < 1e-12
+
+
+@pytest.mark.parametrize("P,n,rs", [(2, 16, 4), (4, 16, 4), (2, 32, 8), (4, 32, 4), (3, 24, 4), (1, 16, 4)])
+def test_fused_residual_restriction_on_slabs(P, n, rs):
+    """EP 2 with PUSH (distributed levels): the residual is restricted in registers; a slab's first coarse row is
+    completed with the previous rank's last-row half-sums, exchanged inside the kernel; the coarse rhs's boundary rows
+    reach the ring neighbours' halo areas."""
+    theta, ops, prm = _setup(n, True)
+    rng = np.random.default_rng(7 * P + n + rs)
+    N = n * n
+    x, b = rng.standard_normal(4 * N), rng.standard_normal(4 * N)
+    r4 = (b - ops.F @ x).reshape(4, n, n)
+    ref = np.stack([O.restrict_u(r4[0]), O.restrict_v(r4[1]), O.restrict_u(r4[2]), O.restrict_v(r4[3])])  # [4][nc][nc]
+    got, rows = emu.slab_residual_restrict(P, n, prm, theta, x, b, rs=rs)
+    assert relerr(got, ref.ravel()) < 1e-13
+    nc, rc = n // 2, n // 2 // P
+    for g in range(P):
+        top = ref[:, (g * rc - 1) % nc, :]        # the previous rank's last coarse row
+        bot = ref[:, ((g + 1) * rc) % nc, :]      # the next rank's first coarse row
+        assert relerr(rows[g, 0], top) < 1e-13 and relerr(rows[g, 1], bot) < 1e-13
