@@ -20,6 +20,7 @@
 #include "coarse.cuh"
 #include "stencil.cuh"
 #include "stokes.cuh"
+#include "cell.cuh"
 
 using namespace mpbp;
 
@@ -61,6 +62,7 @@ struct Level {
   bool dist = false;  // slab-distributed over ranks (needs halo exchange); false = whole grid on this rank
   Geo geo{};   // strip geometry for the register-heavy k_stokes kernels (~5 blocks/SM)
   Geo geo4{};  // ... for the 128-register variants (prolongation fused into the sweep: 4 blocks/SM)
+  Geo geoR{};  // ... for the residual + restriction variant (28-column warp tiles: more blocks per strip)
   Geo geoL{};  // strip geometry for the light kernels (k_poisson, k_div, k_grad, k_jacobi0_F: 12-16 blocks/SM)
   Phys ph{};
   double* th = nullptr;    // padded theta: (rows+2) x n
@@ -128,6 +130,7 @@ struct mpbp_plan {
   // rows to the neighbours; the next stencil kernel on that vector then skips its k_halo_push
   bool push_fused = true;
   const double* pending_push = nullptr;  // vector whose halo rows the last kernel already pushed
+  int cell_n = 256;  // whole-grid levels below level 0 with n <= cell_n use the cell-parallel kernels of cell.cuh (MPBP_CELL)
   int coarse_n = 0;  // experimental (MPBP_COARSE=<n>): whole-grid levels with n <= coarse_n run as ONE persistent kernel
   bool fused_mgs = true;
   bool lowsync = true;  // FGMRES orthogonalisation: low-synchronisation Gram-Schmidt (MPBP_ORTH=mgs: modified Gram-Schmidt)
@@ -400,7 +403,7 @@ static void sx_launch(mpbp_plan* p, dim3 grid, const StokesArgs& a) {
 static int launch_sx(mpbp_plan* p, int l, SxKind k, StokesArgs& a) {
   Level& v = p->lev[l];
   a.th = v.th;
-  a.g = (k.in == 2) ? v.geo4 : v.geo;
+  a.g = (k.in == 2) ? v.geo4 : (k.ep == 2 ? v.geoR : v.geo);
   a.ph = v.ph;
   const int wc = (k.ep == 2) ? WarpTile<2>::cols : WarpTile<0>::cols;
   if ((k.in == 2 || k.ep == 2) && ((v.rows & 1) || (a.g.rs & 1) || (a.g.re & 1) || (v.dist && k.ep == 2 && !k.push)))
@@ -431,11 +434,51 @@ static int launch_sx(mpbp_plan* p, int l, SxKind k, StokesArgs& a) {
   return 0;
 }
 
+// ---- small whole-grid levels: cell-parallel kernels (csrc/cell.cuh), one load round trip per launch ----
+static inline bool use_cell(const mpbp_plan* p, int l) {
+  const Level& v = p->lev[l];
+  return l > 0 && !v.dist && v.n <= p->cell_n && !(v.n & 1) && v.ph.mass_mode == 0;
+}
+static CellArgs cell_args(mpbp_plan* p, int l) {
+  Level& v = p->lev[l];
+  CellArgs a{};
+  a.th = v.th;
+  a.ph = v.ph;
+  a.n = v.n;
+  a.omega = p->cfg.omega;
+  return a;
+}
+static inline dim3 cell_grid(int nx, int ny) { return dim3((nx + kCellBX - 1) / kCellBX, (ny + kCellBY - 1) / kCellBY); }
+// in: 0 sweep of x, 1 pre-smoothing pair from b, 2 prolongation + sweep, 3 residual + restriction
+static int cell_launch(mpbp_plan* p, int l, int in, const double* x, const double* b, double* y) {
+  Level& v = p->lev[l];
+  CellArgs a = cell_args(p, l);
+  a.x = x;
+  a.b = b;
+  a.y = y;
+  a.wd = v.wdF;
+  const dim3 block(kCellBX * kCellBY);
+  if (in == 3) {
+    a.bc = p->lev[l + 1].bF;
+    k_cell_rr<<<cell_grid(v.n / 2, v.n / 2), block, 0, p->st>>>(a);
+  } else if (in == 2) {
+    a.ec = p->lev[l + 1].xF;
+    k_cell_sweep<2><<<cell_grid(v.n, v.n), block, 0, p->st>>>(a);
+  } else if (in == 1) {
+    k_cell_sweep<1><<<cell_grid(v.n, v.n), block, 0, p->st>>>(a);
+  } else {
+    k_cell_sweep<0><<<cell_grid(v.n, v.n), block, 0, p->st>>>(a);
+  }
+  LAUNCH_CHECK(p);
+  return 0;
+}
+
 // y = Op x (mode 0), b - F x (mode 1), x + omega (b - F x)/diag (mode 2); optional Chebyshev epilogue on mode 2.
 // On distributed levels the smoothing / residual kernels push their own boundary rows to the ring neighbours.
 static int op_stokes(mpbp_plan* p, int l, int mode, bool with_p, const double* x, const double* b, double* y,
                      double omega, const ChebEp* ce = nullptr, bool stash = false) {
   Level& v = p->lev[l];
+  if (mode == 2 && !with_p && !ce && omega == p->cfg.omega && use_cell(p, l)) return cell_launch(p, l, 0, x, b, y);
   StokesArgs a{};
   RET(make_view(p, v, x, with_p ? 5 : 4, a.xin, stash));
   a.b = b;
@@ -462,6 +505,7 @@ static int op_jacobi0_F(mpbp_plan* p, int l, const double* b, double* y, double 
 // x2 = x1 + wd (b - F x1), x1 = wd b: the two pre-smoothing sweeps from a zero guess in one pass over b
 static int op_presmooth_pair(mpbp_plan* p, int l, const double* b, double* y) {
   Level& v = p->lev[l];
+  if (use_cell(p, l)) return cell_launch(p, l, 1, nullptr, b, y);
   StokesArgs a{};
   RET(make_view(p, v, b, 4, a.xin));
   a.wd.x = v.wdF;
@@ -491,6 +535,7 @@ static int op_presmooth_pair(mpbp_plan* p, int l, const double* b, double* y) {
 static int op_residual_restrict(mpbp_plan* p, int l, const double* x, const double* b, bool stash) {
   Level& v = p->lev[l];
   Level& c = p->lev[l + 1];
+  if (use_cell(p, l)) return cell_launch(p, l, 3, x, b, nullptr);
   const bool gather = v.dist && (l + 1 == p->first_repl);
   StokesArgs a{};
   RET(make_view(p, v, x, 4, a.xin, stash));
@@ -517,6 +562,7 @@ static int op_prolong_sweep(mpbp_plan* p, int l, const double* x, const double* 
                             const ChebEp* ce) {
   Level& v = p->lev[l];
   Level& c = p->lev[l + 1];
+  if (!ce && omega == p->cfg.omega && use_cell(p, l)) return cell_launch(p, l, 2, x, b, y);
   StokesArgs a{};
   if (v.dist) {
     // x's halo rows were stashed by the residual kernel of this cycle (the comm slots have been recycled since)
@@ -934,7 +980,7 @@ static int vcycle(mpbp_plan* p, int l, bool isF, const double* b, double* x, con
   }
   double* t = isF ? v.tF : v.tP;
   double* r = isF ? v.rF : v.rP;
-  const bool even = !(v.rows & 1) && !(v.geo.rs & 1) && !(v.geo4.rs & 1);
+  const bool even = !(v.rows & 1) && !(v.geo.rs & 1) && !(v.geo4.rs & 1) && !(v.geoR.rs & 1);
   const bool dist_ok = !v.dist || (p->p2p && p->push_fused);  // distributed levels: fused variants need the peer-memory halos
   const bool fuse_pre = isF && (p->fuse & 1) && dist_ok && c.nu1 == 2 && v.wdF != nullptr;
   // residual + restriction (slabs: peer-memory halos and at least two coarse rows per rank)
@@ -1349,6 +1395,7 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
   if (const char* e = getenv("MPBP_ORTH")) p->lowsync = strcmp(e, "mgs") != 0;
   if (const char* e = getenv("MPBP_FUSE")) p->fuse = atoi(e);
   if (const char* e = getenv("MPBP_COARSE")) p->coarse_n = atoi(e);
+  if (const char* e = getenv("MPBP_CELL")) p->cell_n = atoi(e);  // 0: marching kernels on every level
   if (const char* e = getenv("MPBP_PUSH_FUSED")) p->push_fused = atoi(e) != 0;
   if (cudaMemsetAsync(p->counter, 0, 64 * sizeof(unsigned int), nullptr) != cudaSuccess ||
       cudaMemsetAsync(p->dseq, 0, 16 * sizeof(unsigned long long), nullptr) != cudaSuccess)
@@ -1437,20 +1484,30 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
       if (const char* e = getenv("MPBP_PF")) v.geo.pf = std::max(0, std::min(atoi(e), 64));
       v.geo4 = v.geo;
       v.geoL = v.geo;
+      v.geoR = v.geo;
+      const int gxR = (n + WarpTile<2>::cols * kBlockWarps - 1) / (WarpTile<2>::cols * kBlockWarps);
       // single-wave decomposition (set_strips): measured SLOWER than uniform 32-row strips on one B200 at 4096^2
       // (Jacobi sweep 0.344 ms vs 0.290 ms, profiles/r2_tuning.txt) -- off unless MPBP_WAVE=1
       const bool wave = getenv("MPBP_WAVE") && atoi(getenv("MPBP_WAVE")) != 0;
       if (wave) {
         set_strips(v.geo, gx, v.rows, 5 * sms_);
         set_strips(v.geo4, gx, v.rows, 4 * sms_);
+        set_strips(v.geoR, gxR, v.rows, 5 * sms_);
       } else {
-        v.geo.rs = v.geo4.rs = choose_rs(gx, v.rows, 5 * sms_);
-        if (!(v.rows & 1) && (v.geo.rs & 1)) v.geo.rs = (v.geo4.rs += 1);
+        // every variant gets the strip height that fills whole waves of ITS resident-block count and grid width:
+        // on the slabs of 2-8 GPUs a launch is one or two waves, and a shared height cost the 4-blocks/SM and the
+        // 28-column variants a nearly empty extra wave
+        v.geo.rs = choose_rs(gx, v.rows, 5 * sms_);
+        v.geo4.rs = choose_rs(gx, v.rows, 4 * sms_);
+        v.geoR.rs = choose_rs(gxR, v.rows, 5 * sms_);
+        for (Geo* g : {&v.geo, &v.geo4, &v.geoR})
+          if (!(v.rows & 1) && (g->rs & 1)) g->rs += 1;
       }
       if (const char* e = getenv("MPBP_RS")) {
-        v.geo.rs = v.geo4.rs = std::max(1, std::min(atoi(e), v.rows));
-        if (!(v.rows & 1) && (v.geo.rs & 1)) v.geo.rs = (v.geo4.rs += 1);
-        v.geo.re = v.geo4.re = 0;
+        v.geo.rs = std::max(1, std::min(atoi(e), v.rows));
+        if (!(v.rows & 1) && (v.geo.rs & 1)) v.geo.rs += 1;
+        v.geo4.rs = v.geoR.rs = v.geo.rs;
+        v.geo.re = v.geo4.re = v.geoR.re = 0;
       }
       {  // light kernels (16 resident blocks/SM)
         int rs = 32;
@@ -1750,7 +1807,7 @@ static double vcycle_bytes(const mpbp_plan* p, int l, bool isF, bool with_ep) {
   const double N = (double)p->lev[l].fs();
   if (l == L - 1) return 0.0;  // dense coarse solve: negligible
   const Level& v = p->lev[l];
-  const bool even = !(v.rows & 1) && !(v.geo.rs & 1) && !(v.geo4.rs & 1);
+  const bool even = !(v.rows & 1) && !(v.geo.rs & 1) && !(v.geo4.rs & 1) && !(v.geoR.rs & 1);
   double by = 0.0;
   // the epilogue replaces the write of z (4N or N doubles) by read d, x + write d, x (upper bound: middle cycles)
   const double ep_extra = with_ep ? (isF ? 4 : 1) * 8.0 * N * 3.0 : 0.0;

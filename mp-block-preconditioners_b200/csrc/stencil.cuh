@@ -631,16 +631,36 @@ __global__ void __launch_bounds__(256) k_dense_matvec(const double* __restrict__
   const int row = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= m) return;
   const double* __restrict__ mr = M + (size_t)row * m;
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  int k = lane;
-  for (; k + 96 < m; k += 128) {
-    a0 = fma(mr[k], x[k], a0);
-    a1 = fma(mr[k + 32], x[k + 32], a1);
-    a2 = fma(mr[k + 64], x[k + 64], a2);
-    a3 = fma(mr[k + 96], x[k + 96], a3);
+  double acc = 0.0;
+  if ((m & 63) == 0) {
+    // 16-byte loads, eight of them in flight per lane: the matrix is usually NOT L2-resident (a V-cycle streams
+    // gigabytes between two coarse solves), so the kernel is one DRAM latency plus 8 MB / all SMs
+    const double2* __restrict__ m2 = reinterpret_cast<const double2*>(mr);
+    const double2* __restrict__ x2 = reinterpret_cast<const double2*>(x);
+    const int h = m >> 1;  // double2 elements per row
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int k = lane; k < h; k += 256) {
+      double2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (k + 32 * u < h) ? m2[k + 32 * u] : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < 8; u += 2) {
+        if (k + 32 * u < h) {
+          const double2 xa = x2[k + 32 * u];
+          a0 = fma(v[u].x, xa.x, a0);
+          a1 = fma(v[u].y, xa.y, a1);
+        }
+        if (k + 32 * (u + 1) < h) {
+          const double2 xb = x2[k + 32 * (u + 1)];
+          a2 = fma(v[u + 1].x, xb.x, a2);
+          a3 = fma(v[u + 1].y, xb.y, a3);
+        }
+      }
+    }
+    acc = (a0 + a1) + (a2 + a3);
+  } else {
+    for (int k = lane; k < m; k += 32) acc = fma(mr[k], x[k], acc);
   }
-  for (; k < m; k += 32) a0 = fma(mr[k], x[k], a0);
-  double acc = (a0 + a1) + (a2 + a3);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
   if (lane == 0) y[row] = acc;

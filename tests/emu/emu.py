@@ -12,6 +12,7 @@ OUT = os.path.join(HERE, "_build", "libmpbp_emu.so")
 SRCS = [os.path.join(HERE, "emu_kernels.cpp"), os.path.join(HERE, "cuda_emu.h"),
         os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "stencil.cuh"),
         os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "ll.cuh"),
+        os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "cell.cuh"),
         os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "coarse.cuh"),
         os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "stokes.cuh")]
 _dp = C.POINTER(C.c_double)
@@ -173,3 +174,13 @@ def slab_residual_restrict(P, n, prm, theta, x, b, rs=4):
     rows = np.zeros((P, 2, 4, nc))
     load().emu_slab_residual_restrict(P, n, _p(prm), _p(th), _p(x), _p(b), _p(out), _p(rows), rs)
     return out, rows
+
+
+def cell(IN, n, prm, theta, x=None, b=None, wd=None, ec=None, omega=0.8):
+    """csrc/cell.cuh: k_cell_sweep<IN> (IN 0/1/2) or k_cell_rr (IN 3) on a whole-grid level with face-average mass."""
+    c = lambda v: None if v is None else np.ascontiguousarray(v, dtype=np.float64)
+    x, b, wd, ec = c(x), c(b), c(wd), c(ec)
+    thp = pad_theta(theta)
+    out = np.zeros(n * n if IN == 3 else 4 * n * n)
+    load().emu_cell(IN, n, _p(prm), _p(thp), _p(x), _p(b), _p(wd), _p(ec), _p(out), C.c_double(omega))
+    return out

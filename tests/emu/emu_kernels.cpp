@@ -4,6 +4,7 @@
 #include "../../mp-block-preconditioners_b200/csrc/stencil.cuh"
 #include "../../mp-block-preconditioners_b200/csrc/coarse.cuh"
 #include "../../mp-block-preconditioners_b200/csrc/stokes.cuh"
+#include "../../mp-block-preconditioners_b200/csrc/cell.cuh"
 
 using namespace mpbp;
 
@@ -520,6 +521,24 @@ void emu_slab_residual_restrict(int P, int n, const double* prm, const double* t
         out_rows[((size_t)g * 2 + dir) * 4 * nc + i] = (e[i].tag == dseq[g]) ? e[i].v : std::nan("");
     }
   }
+}
+
+// csrc/cell.cuh: the cell-parallel kernels of the small whole-grid levels.  in: 0 sweep, 1 pre-smoothing pair,
+// 2 prolongation + sweep, 3 residual + restriction (out: 4 * (n/2)^2 values).
+void emu_cell(int in, int n, const double* prm, const double* th_pad, const double* x, const double* b, const double* wd,
+              const double* ec, double* out, double omega) {
+  Tables t;
+  CellArgs a{};
+  a.th = th_pad;
+  a.ph = make_phys(n, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], prm[6], 0, t);
+  a.n = n;
+  a.x = x; a.b = b; a.wd = wd; a.ec = ec; a.y = out; a.bc = out; a.omega = omega;
+  const dim3 block(kCellBX * kCellBY);
+  auto grid = [](int nx, int ny) { return dim3((nx + kCellBX - 1) / kCellBX, (ny + kCellBY - 1) / kCellBY); };
+  if (in == 3) emu::launch(grid(n / 2, n / 2), block, [&] { k_cell_rr(a); });
+  else if (in == 2) emu::launch(grid(n, n), block, [&] { k_cell_sweep<2>(a); });
+  else if (in == 1) emu::launch(grid(n, n), block, [&] { k_cell_sweep<1>(a); });
+  else emu::launch(grid(n, n), block, [&] { k_cell_sweep<0>(a); });
 }
 
 }  // extern "C"

@@ -222,3 +222,26 @@ def test_fused_residual_restriction_on_slabs(P, n, rs):
         top = ref[:, (g * rc - 1) % nc, :]        # the previous rank's last coarse row
         bot = ref[:, ((g + 1) * rc) % nc, :]      # the next rank's first coarse row
         assert relerr(rows[g, 0], top) < 1e-13 and relerr(rows[g, 1], bot) < 1e-13
+
+
+@pytest.mark.parametrize("n", [8, 12, 36, 64])
+def test_cell_parallel_kernels_of_the_small_levels(n):
+    """csrc/cell.cuh: one thread per cell, the same fused variants as the marching kernels (levels below 0: face-average
+    mass term, user-style theta), against compositions of the oracle's operators."""
+    theta, ops, prm = _setup(n, False)
+    rng = np.random.default_rng(n)
+    N = n * n
+    x, b = rng.standard_normal(4 * N), rng.standard_normal(4 * N)
+    dg = ops.F.diagonal()
+    sweep = lambda v: v + 0.8 * (b - ops.F @ v) / dg
+    assert relerr(emu.cell(0, n, prm, theta, x=x, b=b), sweep(x)) < 1e-13
+    assert relerr(emu.cell(1, n, prm, theta, b=b, wd=0.8 / dg), sweep(0.8 * b / dg)) < 1e-13
+    ec = rng.standard_normal(N)
+    e4 = ec.reshape(4, n // 2, n // 2)
+    xt = x + np.concatenate([O.prolong_u(e4[0]).ravel(), O.prolong_v(e4[1]).ravel(), O.prolong_u(e4[2]).ravel(),
+                             O.prolong_v(e4[3]).ravel()])
+    assert relerr(emu.cell(2, n, prm, theta, x=x, b=b, ec=ec), sweep(xt)) < 1e-13
+    r4 = (b - ops.F @ x).reshape(4, n, n)
+    ref_r = np.concatenate([O.restrict_u(r4[0]).ravel(), O.restrict_v(r4[1]).ravel(), O.restrict_u(r4[2]).ravel(),
+                            O.restrict_v(r4[3]).ravel()])
+    assert relerr(emu.cell(3, n, prm, theta, x=x, b=b), ref_r) < 1e-13
