@@ -63,7 +63,7 @@ typedef struct mpbp_config {
   int project;            /* 1: remove the mean from every (GtG)~^-1 result (constant null space, solve.py:260-264) */
   int operators_only;     /* 1: no multigrid hierarchy (operator applies only; sub-solves return MPBP_E_STATE) */
   int dist_min_n;         /* nranks>1: multigrid levels with n < dist_min_n are replicated on every rank (all-gather
-                             of the restricted residual) instead of slab-distributed; 0 = default (1024) */
+                             of the restricted residual) instead of slab-distributed; 0 = default (512) */
   /* optional caller-owned DEVICE workspace (e.g. a torch tensor); NULL = the plan cudaMallocs */
   void* workspace;
   size_t workspace_bytes;

@@ -49,7 +49,7 @@ class SubSolver:
     lmin: float = 0.75
     lmax: float = 1.2
     project: bool = True
-    dist_min_n: int = 0  # multi-GPU: levels with n < dist_min_n are replicated (0 = library default 1024)
+    dist_min_n: int = 0  # multi-GPU: levels with n < dist_min_n are replicated (0 = library default 512)
 
 
 def _stream_ptr(device):

@@ -1,6 +1,7 @@
 """Compact per-kernel table from an .ncu-rep: for every distinct kernel name the launch with the LARGEST grid (the
 level-0 instance of a multigrid kernel), with the metrics the roofline discussion uses.
-    python profiles/ncu_table.py gpurun_out/prof.ncu-rep [more.ncu-rep ...]"""
+    python profiles/ncu_table.py gpurun_out/prof.ncu-rep [more.ncu-rep ...] [--traffic profiles/r2_ncu_traffic.json]
+--traffic writes dram__bytes_read/write of the level-0 damped-Jacobi sweep (bench.py's roofline kernel) for bench.py."""
 import csv
 import json
 import re
@@ -28,7 +29,13 @@ def to_bytes(val, unit):
 
 def main():
     out = {}
-    for rep in sys.argv[1:]:
+    args = list(sys.argv[1:])
+    traffic = None
+    if "--traffic" in args:
+        i = args.index("--traffic")
+        traffic = args[i + 1]
+        del args[i:i + 2]
+    for rep in args:
         raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(raw.splitlines()))
         hdr, units = rows[0], rows[1]
@@ -60,7 +67,16 @@ def main():
     print(f"{'kernel':58s} " + " ".join(f"{s:>8s}" for s in names))
     for name, rec in out.items():
         print(f"{name[:58]:58s} " + " ".join(f"{rec.get(s, float('nan')):8.1f}" for s in names) + "  grid " + rec["grid"])
-    json.dump(out, open("/dev/stdout", "w") if False else open(sys.argv[1] + ".table.json", "w"), indent=1)
+    json.dump(out, open(args[0] + ".table.json", "w"), indent=1)
+    if traffic:
+        for name, rec in out.items():
+            if re.search(r"k_stokes_x<0, 2, (false|0), 0, (false|0)", name) and "rdMB" in rec:
+                g = [int(t) for t in re.findall(r"\d+", rec["grid"])]
+                json.dump({"kernel": name, "grid": rec["grid"], "n": 4096 if g[:2] == [35, 128] else None,
+                           "dram_bytes_read": rec["rdMB"] * 1e6, "dram_bytes_write": rec["wrMB"] * 1e6,
+                           "time_us_under_ncu": rec.get("us"), "source": "ncu --set full capture " + " ".join(args)},
+                          open(traffic, "w"), indent=1)
+                break
 
 
 if __name__ == "__main__":

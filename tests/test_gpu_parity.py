@@ -403,6 +403,33 @@ def test_fused_smoothing_kernels_vs_oracle(mp, monkeypatch, fuse, n, eta_n):
     assert relerr(M @ v, Mo.matvec(v)) < 1e-9
 
 
+@pytest.mark.parametrize("cell", ["0", "64", "512"])
+@pytest.mark.parametrize("n,eta_n,n_coarse", [(128, 1e3, 4), (96, 10.0, 4), (256, 1e4, 16)])
+def test_cell_parallel_small_level_kernels_vs_oracle(mp, monkeypatch, cell, n, eta_n, n_coarse):
+    """MPBP_CELL: whole-grid levels below level 0 with n <= MPBP_CELL run the cell-parallel kernels of csrc/cell.cuh
+    (one thread per cell) instead of the marching kernels; 0 switches them off.  Same V-cycle: the oracle tolerances
+    apply for every setting, and the settings agree with each other far below them.  n_coarse = 16 is the benchmarked
+    hierarchy (dense solve on the 16 x 16 grid, warp-per-row kernel)."""
+    monkeypatch.setenv("MPBP_CELL", cell)
+    xi, eta_s, c, d = 1.0, 1.0, 1.0, -1.0
+    sub = mp.SubSolver(kind="mg", F_cycles=3, P_cycles=2, cheb=True, n_coarse=n_coarse)
+    bp = mp.MultiphaseBlockPreconditioner(n, xi, eta_n, eta_s, sub_solver=sub)
+    p = bp.plan(c, d)
+    monkeypatch.delenv("MPBP_CELL")
+    ops = O.Operators(n, xi, eta_n, eta_s, c, d)
+    rng = np.random.default_rng(5)
+    N = n * n
+    v = rng.standard_normal(5 * N)
+    v[4 * N:] -= v[4 * N:].mean()
+    mg1 = O.Multigrid(ops, O.SubSolverConfig(kind="mg", cycles=1, n_coarse=n_coarse))
+    assert relerr(p.call("mpbp_vcycle_F", v[:4 * N], 4 * N, 4 * N), mg1._vcycle("F", 0, v[:4 * N])) < 1e-10
+    Mo = O.ApproxSchur(ops, O.SubSolverConfig(kind="mg", cycles=3, cheb=True, n_coarse=n_coarse))
+    cfgP = O.SubSolverConfig(kind="mg", cycles=2, cheb=True, n_coarse=n_coarse)
+    Mo.P_inv = O.SubSolver(ops, "P", cfgP, O.Multigrid(ops, cfgP))
+    M = bp.approx_schur_operator(c, d)
+    assert relerr(M @ v, Mo.matvec(v)) < 1e-9
+
+
 @pytest.mark.skipif(os.environ.get("MPBP_TEST_EXPERIMENTAL") != "1",
                     reason="experimental persistent coarse V-cycle kernel (off by default); set MPBP_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("n,eta_n", [(64, 1e3), (128, 10.0)])
