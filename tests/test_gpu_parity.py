@@ -422,7 +422,10 @@ def test_cell_parallel_small_level_kernels_vs_oracle(mp, monkeypatch, cell, n, e
     v = rng.standard_normal(5 * N)
     v[4 * N:] -= v[4 * N:].mean()
     mg1 = O.Multigrid(ops, O.SubSolverConfig(kind="mg", cycles=1, n_coarse=n_coarse))
-    assert relerr(p.call("mpbp_vcycle_F", v[:4 * N], 4 * N, 4 * N), mg1._vcycle("F", 0, v[:4 * N])) < 1e-10
+    # two correct dense inverses of the coarsest velocity block (Gauss-Jordan here, LAPACK in the oracle) differ by
+    # eps * cond, cond ~ 260 * eta_n/eta_s * (n_coarse/4)^2 (cf. tests/test_c_oracle.py): measured 2.2e-10 at 1e4, 16
+    tolF = max(1e-10, 2e-13 * eta_n * (n_coarse / 4) ** 2)
+    assert relerr(p.call("mpbp_vcycle_F", v[:4 * N], 4 * N, 4 * N), mg1._vcycle("F", 0, v[:4 * N])) < tolF
     Mo = O.ApproxSchur(ops, O.SubSolverConfig(kind="mg", cycles=3, cheb=True, n_coarse=n_coarse))
     cfgP = O.SubSolverConfig(kind="mg", cycles=2, cheb=True, n_coarse=n_coarse)
     Mo.P_inv = O.SubSolver(ops, "P", cfgP, O.Multigrid(ops, cfgP))
