@@ -502,8 +502,9 @@ def run_apply_sweep(args):
                             "apply_A": {"ms": ms_ax, "algorithmic_bytes": ax_bytes, "gbs": ax_bytes / ms_ax / 1e6,
                                         "frac_per_gpu": ax_bytes / ms_ax / 1e6 / world / peak}},
                 "comm": {"halo_exchange_us": hu.value, "allreduce_us": au.value,
-                         "note": "one level-0 halo exchange of a 5-field vector (peer-memory push + flag wait) and one "
-                                 "scalar all-reduce, 200 back-to-back repetitions each"},
+                         "note": "one level-0 halo exchange of a 5-field vector (push kernel + fetching consumer kernel, "
+                                 "LL peer-memory protocol) and one scalar all-reduce (one-block reduction kernel with the "
+                                 "fused peer-memory all-reduce), 200 repetitions each replayed from a CUDA graph"},
                 "clocks": clocks, "gpu_launches": int(launches)}
         _emit(line)
     sys.stdout.flush()

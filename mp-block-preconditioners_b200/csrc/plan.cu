@@ -1732,7 +1732,9 @@ extern "C" int mpbp_precond_apply(mpbp_plan* p, const double* v, double* z, void
 }
 
 // Communication probe (bench.py --workload apply8192): average time of one level-0 halo exchange of a 5-field vector
-// (push + a consumer that only waits) and of one scalar all-reduce, in microseconds, measured with CUDA events.
+// (push kernel + a consumer kernel that only fetches the rows) and of one scalar all-reduce (a one-block reduction
+// kernel with the fused peer-memory all-reduce), in microseconds.  The repetitions are replayed from a CUDA graph --
+// the regime the preconditioner apply runs in -- and timed with CUDA events.
 extern "C" int mpbp_comm_probe(mpbp_plan* p, int reps, double* halo_us, double* allreduce_us, void* stream) {
   ENTER(p, stream);
   auto body = [&]() -> int {
@@ -1743,35 +1745,46 @@ extern "C" int mpbp_comm_probe(mpbp_plan* p, int reps, double* halo_us, double* 
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
-    float ms = 0.f;
-    for (int pass = 0; pass < 2; ++pass) {  // pass 0: warm-up
-      CU(cudaEventRecord(e0, p->st));
-      for (int i = 0; i < reps; ++i) {
-        VecIn in{};
-        p->pending_push = nullptr;
-        RET(make_view(p, v, p->vin, 5, in));
-        if (p->p2p) {
-          k_halo_consume<<<(v.n + 255) / 256, 256, 0, p->st>>>(in, 5, v.n, p->scal + kScal - 2);
-          LAUNCH_CHECK(p);
+    for (int what = 0; what < 2; ++what) {
+      CU(cudaStreamBeginCapture(p->st, cudaStreamCaptureModeThreadLocal));
+      int rc = 0;
+      for (int i = 0; i < reps && rc == 0; ++i) {
+        if (what == 0) {
+          VecIn in{};
+          p->pending_push = nullptr;
+          rc = make_view(p, v, p->vin, 5, in);
+          if (rc == 0 && p->p2p) {
+            k_halo_consume<<<(v.n + 255) / 256, 256, 0, p->st>>>(in, 5, v.n, p->scal + kScal - 2);
+            p->launches++;
+          }
+        } else {
+          k_sum<<<1, kRedThreads, 0, p->st>>>(p->vin, 1024, p->partial, p->counter, p->scal + kScal - 2, p->red);
+          p->launches++;
+          if (p->red.nranks <= 1) rc = allreduce_scal(p, p->scal + kScal - 2, 1);
         }
       }
-      CU(cudaEventRecord(e1, p->st));
-      CU(cudaEventSynchronize(e1));
-      CU(cudaEventElapsedTime(&ms, e0, e1));
-    }
-    *halo_us = 1e3 * ms / reps;
-    for (int pass = 0; pass < 2; ++pass) {
-      CU(cudaEventRecord(e0, p->st));
-      for (int i = 0; i < reps; ++i) {
-        k_sum<<<1, kRedThreads, 0, p->st>>>(p->vin, 1024, p->partial, p->counter, p->scal + kScal - 2, p->red);
-        LAUNCH_CHECK(p);
-        if (p->red.nranks <= 1) RET(allreduce_scal(p, p->scal + kScal - 2, 1));
+      cudaGraph_t g = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(p->st, &g);
+      if (rc != 0) {
+        if (g) cudaGraphDestroy(g);
+        return rc;
       }
-      CU(cudaEventRecord(e1, p->st));
-      CU(cudaEventSynchronize(e1));
-      CU(cudaEventElapsedTime(&ms, e0, e1));
+      CU(ce);
+      cudaGraphExec_t ge = nullptr;
+      CU(cudaGraphInstantiate(&ge, g, 0));
+      cudaGraphDestroy(g);
+      float ms = 0.f;
+      for (int pass = 0; pass < 2; ++pass) {  // pass 0: warm-up
+        CU(cudaEventRecord(e0, p->st));
+        CU(cudaGraphLaunch(ge, p->st));
+        CU(cudaEventRecord(e1, p->st));
+        CU(cudaEventSynchronize(e1));
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+      }
+      cudaGraphExecDestroy(ge);
+      (what == 0 ? *halo_us : *allreduce_us) = 1e3 * ms / reps;
     }
-    *allreduce_us = 1e3 * ms / reps;
+    p->pending_push = nullptr;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return 0;

@@ -94,6 +94,20 @@ __device__ __forceinline__ void halo_fetch_cols(double* land, char* comm, size_t
     if (need_bot) land[e + 5 * n] = WARP ? ll_wait_warp(ll_bot + e, s) : ll_wait(ll_bot + e, s);
   }
 }
+#ifdef MPBP_EMU
+#define MPBP_NOINLINE
+#else
+#define MPBP_NOINLINE __noinline__
+#endif
+// out-of-line copy for the light kernels (k_poisson, k_div, k_grad: 32 registers, 16 blocks/SM -- the inlined polling
+// loop cost k_poisson<2> eight registers and a quarter of its occupancy)
+__device__ MPBP_NOINLINE void halo_fetch_warp_noinline(double* land, char* comm, size_t area, const unsigned long long* dseq,
+                                                       int nk, int n, int col, bool need_top, bool need_bot) {
+  halo_fetch_cols<true>(land, comm, area, dseq, 0, nk, 1, n, col, need_top, need_bot);
+}
+__device__ __forceinline__ void halo_fetch_light(const VecIn& v, int nk, int n, int col, bool need_top, bool need_bot) {
+  if (v.dseq != nullptr) halo_fetch_warp_noinline(v.land, v.comm, v.area, v.dseq, nk, n, col, need_top, need_bot);
+}
 template <bool WARP = false>
 __device__ __forceinline__ void halo_fetch(const VecIn& v, int k0, int nk, int kstep, int n, int col, bool need_top,
                                            bool need_bot) {
@@ -377,8 +391,10 @@ __global__ void __launch_bounds__(kBlockThreads) k_jacobi0_F(const double* __res
 // ------------------------------------------------------------------------------------------
 //   CHEB (MODE 2): the sweep's result z goes through the Chebyshev epilogue (ChebEp) instead of being stored
 //   PUSH: the result's first / last rows also go to the ring neighbours (see PushOut)
+//   (the plain variants are capped at 32 registers, i.e. 16 resident blocks per SM: these kernels consume their loads in
+//   the iteration that issues them and live off occupancy)
 template <int MODE, bool CHEB = false, bool PUSH = false>
-__global__ void __launch_bounds__(kBlockThreads) k_poisson(VecIn pin, const double* __restrict__ th,
+__global__ void __launch_bounds__(kBlockThreads, (CHEB || PUSH) ? 1 : 16) k_poisson(VecIn pin, const double* __restrict__ th,
                                                            const double* __restrict__ b, double* __restrict__ y,
                                                            Geo g, Phys ph, double omega, ChebEp ce = ChebEp{},
                                                            PushOut po = PushOut{}) {
@@ -388,7 +404,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_poisson(VecIn pin, const doub
   int r0, r1;
   if (!strip_rows(g, r0, r1)) return;
   if (MODE != 3 && (r0 == 0 || r1 == rows)) {
-    halo_fetch<true>(pin, 0, 1, 1, n, c, r0 == 0, r1 == rows);
+    halo_fetch_light(pin, 1, n, c, r0 == 0, r1 == rows);
   }
   PushCtx pc{};
   if (PUSH) pc = push_begin(po, r0 == 0, r1 == rows);
@@ -452,7 +468,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_div(VecIn win, const double* 
   int r0, r1;
   if (!strip_rows(g, r0, r1)) return;
   if (r0 == 0 || r1 == rows) {
-    halo_fetch<true>(win, 0, 4, 1, n, c, r0 == 0, r1 == rows);
+    halo_fetch_light(win, 4, n, c, r0 == 0, r1 == rows);
   }
   double th_m = th_row(th, r0 - 1, n)[c];
   double th_c = th_row(th, r0, n)[c];
@@ -487,7 +503,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_grad(VecIn pin, const double*
   int r0, r1;
   if (!strip_rows(g, r0, r1)) return;
   if (r0 == 0 || r1 == rows) {
-    halo_fetch<true>(pin, 0, 1, 1, n, c, r0 == 0, r1 == rows);
+    halo_fetch_light(pin, 1, n, c, r0 == 0, r1 == rows);
   }
   PushCtx pc{};
   if (PUSH) pc = push_begin(po, r0 == 0, r1 == rows);
