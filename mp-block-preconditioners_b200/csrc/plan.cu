@@ -21,6 +21,7 @@
 #include "stencil.cuh"
 #include "stokes.cuh"
 #include "cell.cuh"
+#include "poisson.cuh"
 
 using namespace mpbp;
 
@@ -73,6 +74,7 @@ struct Level {
   double *gF = nullptr, *gP = nullptr;  // restricted slab before the all-gather (first replicated level only)
   double* wdF = nullptr;                // omega / diag(F), 4N (fused pre-smoothing)
   double* wdh = nullptr;                // dist: the ring neighbours' boundary rows of wdF, [2][4][n] (static)
+  double* wdP = nullptr;                // 1 / diag(GtG), N (fused pressure pre-smoothing; whole-grid levels)
   size_t fs() const { return (size_t)rows * n; }
 };
 
@@ -125,7 +127,7 @@ struct mpbp_plan {
   // V-cycles (rin -> z) replay as CUDA graphs: ~100 small launches per cycle become one graph launch
   // whole-grid levels, MPBP_FUSE overrides: bit 0 fused pre-smoothing pair, bit 1 fused prolongation + first
   // post-sweep, bit 2 fused residual + restriction (csrc/stokes.cuh)
-  int fuse = 7;
+  int fuse = 15;  // bit 3: the same three fusions on the pressure-Poisson cycle (whole-grid levels, csrc/poisson.cuh)
   // experimental (MPBP_PUSH_FUSED=1): smoothing / residual kernels on distributed levels push their own boundary
   // rows to the neighbours; the next stencil kernel on that vector then skips its k_halo_push
   bool push_fused = true;
@@ -219,6 +221,7 @@ static void carve(mpbp_plan* p, Bump& B) {
     if (l < L - 1 && !p->cfg.operators_only) {
       v.wdF = B.take<double>(4 * fs);
       if (v.dist) v.wdh = B.take<double>((size_t)2 * 4 * v.n);
+      if (!v.dist) v.wdP = B.take<double>(fs);
     }
     if (l == p->first_repl) {
       const Level& f = p->lev[l - 1];
@@ -642,6 +645,37 @@ static int op_poisson(mpbp_plan* p, int l, int mode, const double* x, const doub
   if (push) p->pending_push = y;
   return 0;
 }
+// fused pressure-Poisson kernels on whole-grid levels (csrc/poisson.cuh): in 1 pre-smoothing pair from b, 3 residual +
+// restriction (coarse rhs of level l+1), 2 prolongation of level l+1's correction + first post-sweep (optionally the last)
+static int op_poisson_f(mpbp_plan* p, int l, int in, const double* x, const double* b, double* y, const ChebEp* ce) {
+  Level& v = p->lev[l];
+  PoissonFArgs a{};
+  a.x = x;
+  a.b = b;
+  a.wd = v.wdP;
+  a.th = v.th;
+  a.y = y;
+  a.g = v.geoL;
+  a.ph = v.ph;
+  a.omega = p->cfg.omega;
+  const dim3 grid = stencil_grid(v, v.geoL), block(kBlockThreads);
+  if (in == 1) {
+    k_poisson_f<1, 2, 0><<<grid, block, 0, p->st>>>(a);
+  } else if (in == 3) {
+    a.bc = p->lev[l + 1].bP;
+    k_poisson_f<0, 1, 2><<<grid, block, 0, p->st>>>(a);
+  } else {
+    a.ec = p->lev[l + 1].xP;
+    if (ce) {
+      a.ce = *ce;
+      k_poisson_f<2, 2, 1><<<grid, block, 0, p->st>>>(a);
+    } else {
+      k_poisson_f<2, 2, 0><<<grid, block, 0, p->st>>>(a);
+    }
+  }
+  LAUNCH_CHECK(p);
+  return 0;
+}
 // r = scale * D w + add
 static int op_div(mpbp_plan* p, int l, const double* w, const double* add, double* r, double scale) {
   Level& v = p->lev[l];
@@ -984,10 +1018,11 @@ static int vcycle(mpbp_plan* p, int l, bool isF, const double* b, double* x, con
   double* r = isF ? v.rF : v.rP;
   const bool even = !(v.rows & 1) && !(v.geo.rs & 1) && !(v.geo4.rs & 1) && !(v.geoR.rs & 1);
   const bool dist_ok = !v.dist || (p->p2p && p->push_fused);  // distributed levels: fused variants need the peer-memory halos
-  const bool fuse_pre = isF && (p->fuse & 1) && dist_ok && c.nu1 == 2 && v.wdF != nullptr;
+  const bool fuseP = !isF && (p->fuse & 8) && !v.dist && !(v.rows & 1) && !(v.geoL.rs & 1) && v.geoL.re == 0;
+  const bool fuse_pre = isF ? (p->fuse & 1) && dist_ok && c.nu1 == 2 && v.wdF != nullptr : fuseP && c.nu1 == 2 && v.wdP != nullptr;
   // residual + restriction (slabs: peer-memory halos and at least two coarse rows per rank)
-  const bool fuse_rr = isF && (p->fuse & 4) && even && (!v.dist || (dist_ok && v.rows >= 4));
-  const bool fuse_post = isF && (p->fuse & 2) && dist_ok && even && c.nu2 >= 1;  // prolongation + first post-sweep
+  const bool fuse_rr = isF ? (p->fuse & 4) && even && (!v.dist || (dist_ok && v.rows >= 4)) : fuseP;
+  const bool fuse_post = isF ? (p->fuse & 2) && dist_ok && even && c.nu2 >= 1 : fuseP && c.nu2 >= 1;  // prolongation + first post-sweep
   // number of kernels that write the iterate into a fresh buffer (they ping-pong between x and t); the last one
   // must land in x unless it ends in the epilogue
   const int pre_w = fuse_pre ? 1 : c.nu1;
@@ -998,7 +1033,8 @@ static int vcycle(mpbp_plan* p, int l, bool isF, const double* b, double* x, con
   if (c.nu2 == 0 && ce) return set_err(MPBP_E_UNSUPPORTED, "nu2 = 0 is not supported inside the sub-solves");
   // ---- pre-smoothing from a zero guess ----
   if (fuse_pre) {
-    RET(op_presmooth_pair(p, l, b, cur));
+    if (isF) RET(op_presmooth_pair(p, l, b, cur));
+    else RET(op_poisson_f(p, l, 1, nullptr, b, cur, nullptr));
   } else {
     if (isF) RET(op_jacobi0_F(p, l, b, cur, c.omega));
     else RET(op_poisson(p, l, 3, nullptr, b, cur, c.omega));
@@ -1010,7 +1046,8 @@ static int vcycle(mpbp_plan* p, int l, bool isF, const double* b, double* x, con
   }
   // ---- coarse-grid correction ----
   if (fuse_rr) {
-    RET(op_residual_restrict(p, l, cur, b, /*stash=*/fuse_post));
+    if (isF) RET(op_residual_restrict(p, l, cur, b, /*stash=*/fuse_post));
+    else RET(op_poisson_f(p, l, 3, cur, b, nullptr, nullptr));
   } else {
     if (isF) RET(op_stokes(p, l, 1, false, cur, b, r, 0.0, nullptr, /*stash=*/fuse_post));
     else RET(op_poisson(p, l, 1, cur, b, r, 0.0));
@@ -1022,7 +1059,8 @@ static int vcycle(mpbp_plan* p, int l, bool isF, const double* b, double* x, con
   int post = c.nu2;
   if (fuse_post) {
     const bool last = (post == 1);
-    RET(op_prolong_sweep(p, l, cur, b, oth, c.omega, (last && ce) ? ce : nullptr));
+    if (isF) RET(op_prolong_sweep(p, l, cur, b, oth, c.omega, (last && ce) ? ce : nullptr));
+    else RET(op_poisson_f(p, l, 2, cur, b, oth, (last && ce) ? ce : nullptr));
     std::swap(cur, oth);
     post--;
   } else {
@@ -1484,6 +1522,8 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
       cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, dev_);
       v.geo.pf = 3;  // measured best on B200 at 4096^2 (profiles/r1_tuning.txt)
       if (const char* e = getenv("MPBP_PF")) v.geo.pf = std::max(0, std::min(atoi(e), 64));
+      v.geo.pfc = 1;
+      if (const char* e = getenv("MPBP_PFC")) v.geo.pfc = atoi(e) != 0;
       v.geo4 = v.geo;
       v.geoL = v.geo;
       v.geoR = v.geo;
@@ -1546,6 +1586,12 @@ extern "C" int mpbp_plan_create(mpbp_plan** out, const mpbp_config* cfg) {
       if (rc) return fail(rc);
       if (v.dist) {
         rc = fetch_static_halo(p, v, v.wdF, 4, v.wdh);
+        if (rc) return fail(rc);
+      }
+      if (v.wdP) {  // 1 / diag(GtG): the first pressure sweep (omega = 1) applied to ones -- the sweeps' own reciprocal
+        k_fill<<<ew_blocks(v.fs()), 256, 0, p->st>>>(v.tP, 1.0, v.fs());
+        p->launches++;
+        rc = op_poisson(p, (int)l, 3, nullptr, v.tP, v.wdP, 1.0);
         if (rc) return fail(rc);
       }
     }
@@ -1829,16 +1875,17 @@ static double vcycle_bytes(const mpbp_plan* p, int l, bool isF, bool with_ep) {
   if (isF) {
     const bool dist_ok = !v.dist || (p->p2p && p->push_fused);
     const bool fuse_pre = (p->fuse & 1) && dist_ok && c.nu1 == 2 && v.wdF != nullptr;
-    const bool fuse_rr = (p->fuse & 4) && !v.dist && even;
+    const bool fuse_rr = (p->fuse & 4) && even && (!v.dist || (dist_ok && v.rows >= 4));
     const bool fuse_post = (p->fuse & 2) && dist_ok && even && c.nu2 >= 1;
     by += fuse_pre ? 104 * N : 72 * N + (c.nu1 - 1) * 104.0 * N;   // pre-smoothing (pair: reads b, omega/diag, theta)
     by += fuse_rr ? 80 * N : (104 + 40) * N;                         // residual (+ restriction: writes N instead of 4N)
     by += fuse_post ? 112 * N + (c.nu2 - 1) * 104.0 * N              // prolongation fused into the first post-sweep
                     : 72 * N + c.nu2 * 104.0 * N;                    // x += P e ; nu2 sweeps
   } else {
-    by += 24 * N + (c.nu1 - 1) * 32.0 * N;
-    by += 32 * N + 10 * N;
-    by += 18 * N + c.nu2 * 32.0 * N;
+    const bool fuseP = (p->fuse & 8) && !v.dist && !(v.rows & 1) && !(v.geoL.rs & 1) && v.geoL.re == 0;
+    by += (fuseP && c.nu1 == 2 && v.wdP) ? 32 * N : 24 * N + (c.nu1 - 1) * 32.0 * N;   // pair: b, omega/diag, theta, write
+    by += fuseP ? 26 * N : 32 * N + 10 * N;                                            // residual (+ restriction)
+    by += (fuseP && c.nu2 >= 1) ? 34 * N + (c.nu2 - 1) * 32.0 * N : 18 * N + c.nu2 * 32.0 * N;
   }
   return by + ep_extra + vcycle_bytes(p, l + 1, isF, false);
 }

@@ -177,6 +177,7 @@ struct Geo {
   int pf;    // L2 prefetch distance in rows (0 = off)
   int re;    // > 0: the first and last strip are `re` rows short strips and the rows in between are cut into strips of
              // `rs` rows (single-wave decomposition, see strip_rows); 0: uniform strips of `rs` rows
+  int pfc;   // 1: the prolongation + sweep variant also prefetches the coarse correction's rows into L2 (MPBP_PFC)
 };
 // number of strips (= gridDim.y) of a geometry
 __host__ __device__ __forceinline__ int strip_count(const Geo& g) {

@@ -162,6 +162,13 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
       if (arr >= 1 && arr <= 4 && a.ce.read_d) pfp2 = a.ce.d + (arr - 1) * fs + pfo;
       else if (arr >= 5 && arr <= 8 && a.ce.read_x) pfp2 = a.ce.xk + (arr - 5) * fs + pfo;
     }
+    if (IN == 2 && EP != 1 && !EDGE) {
+      // the coarse correction is first touched here as well (every coarse row serves two fine rows and two lanes, but
+      // its first read is a DRAM miss in the middle of a step whose fine rows were prefetched): lanes 0..7 cover the
+      // <= 2 cache lines per field that the warp's 30 columns map to; the coarse row is added per step
+      const int c_first = __shfl_sync(kFull, c, 0), c_last = __shfl_sync(kFull, c, 31);
+      if (lane < 8 && a.g.pfc) pfp2 = cin.x + (lane >> 1) * (int)cin.fs + (((lane & 1) ? c_last : c_first) >> 1);
+    }
   }
 
   // EP 2 starts one row early (stores off): the v-type restriction of coarse row r0/2 needs the residual of row r0-1
@@ -221,6 +228,7 @@ __device__ __forceinline__ void stokes_march(const StokesArgs& a, const int r0, 
     if (a.g.pf > 0 && r + a.g.pf < min(r1 + 1, rows) && r >= 0) {
       if (pfp) pf_l2(pfp + (size_t)r * n);
       if (EP == 1 && pfp2) pf_l2(pfp2 + (size_t)r * n);
+      if (IN == 2 && EP != 1 && !EDGE && pfp2) pf_l2(pfp2 + (size_t)((r + a.g.pf) >> 1) * nc);
     }
     double bn_u = 0.0, bn_v = 0.0, bs_u = 0.0, bs_v = 0.0;
     if (MODE != 0) {

@@ -13,6 +13,7 @@ SRCS = [os.path.join(HERE, "emu_kernels.cpp"), os.path.join(HERE, "cuda_emu.h"),
         os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "stencil.cuh"),
         os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "ll.cuh"),
         os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "cell.cuh"),
+        os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "poisson.cuh"),
         os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "coarse.cuh"),
         os.path.join(ROOT, "mp-block-preconditioners_b200", "csrc", "stokes.cuh")]
 _dp = C.POINTER(C.c_double)
@@ -184,3 +185,20 @@ def cell(IN, n, prm, theta, x=None, b=None, wd=None, ec=None, omega=0.8):
     out = np.zeros(n * n if IN == 3 else 4 * n * n)
     load().emu_cell(IN, n, _p(prm), _p(thp), _p(x), _p(b), _p(wd), _p(ec), _p(out), C.c_double(omega))
     return out
+
+
+def poisson_f(IN, n, prm, theta, x=None, b=None, wd=None, ec=None, d=None, xk=None, cheb=None, flags=(1, 1, 1), rs=4,
+              omega=0.8):
+    """csrc/poisson.cuh: k_poisson_f -- IN 1 pair, 3 residual + restriction, 2 prolongation + sweep, 4 the same with the
+    Chebyshev epilogue (returns (d, xk))."""
+    c = lambda v: None if v is None else np.ascontiguousarray(v, dtype=np.float64)
+    x, b, wd, ec = c(x), c(b), c(wd), c(ec)
+    thp = pad_theta(theta)
+    out = np.zeros((n // 2) ** 2 if IN == 3 else n * n)
+    if IN == 4:
+        d, xk = np.array(d, dtype=np.float64), np.array(xk, dtype=np.float64)
+    ch = None if cheb is None else np.array(cheb, dtype=np.float64)
+    fl = (C.c_int * 3)(*flags)
+    load().emu_poisson_f(IN, n, _p(prm), _p(thp), _p(x), _p(b), _p(wd), _p(ec), _p(d), _p(xk), _p(ch), fl, _p(out), rs,
+                         C.c_double(omega))
+    return (d, xk) if IN == 4 else out

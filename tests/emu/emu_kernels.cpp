@@ -5,6 +5,7 @@
 #include "../../mp-block-preconditioners_b200/csrc/coarse.cuh"
 #include "../../mp-block-preconditioners_b200/csrc/stokes.cuh"
 #include "../../mp-block-preconditioners_b200/csrc/cell.cuh"
+#include "../../mp-block-preconditioners_b200/csrc/poisson.cuh"
 
 using namespace mpbp;
 
@@ -539,6 +540,29 @@ void emu_cell(int in, int n, const double* prm, const double* th_pad, const doub
   else if (in == 2) emu::launch(grid(n, n), block, [&] { k_cell_sweep<2>(a); });
   else if (in == 1) emu::launch(grid(n, n), block, [&] { k_cell_sweep<1>(a); });
   else emu::launch(grid(n, n), block, [&] { k_cell_sweep<0>(a); });
+}
+
+// csrc/poisson.cuh: fused pressure-Poisson kernels on a whole-grid level.  in: 1 pre-smoothing pair, 3 residual +
+// restriction (out: (n/2)^2 values), 2 prolongation + sweep, 4 prolongation + last sweep with the Chebyshev epilogue
+// (d, xk updated in place; cheb = [ca, cb], flags = [read_d, read_x, write_d]).
+void emu_poisson_f(int in, int n, const double* prm, const double* th_pad, const double* x, const double* b,
+                   const double* wd, const double* ec, double* d, double* xk, const double* cheb, const int* flags,
+                   double* out, int rs, double omega) {
+  Tables t;
+  PoissonFArgs a{};
+  a.x = x; a.b = b; a.wd = wd; a.ec = ec; a.th = th_pad; a.y = out; a.bc = out;
+  a.g = Geo{n, n, 0, rs, 0};
+  a.ph = make_phys(n, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], prm[6], 0, t);
+  a.omega = omega;
+  if (in == 4) a.ce = ChebEp{cheb[0], cheb[1], d, xk, flags[0], flags[1], flags[2]};
+  emu::launch(sgrid(n, rs), dim3(kBlockThreads), [&] {
+    switch (in) {
+      case 1: k_poisson_f<1, 2, 0>(a); break;
+      case 3: k_poisson_f<0, 1, 2>(a); break;
+      case 2: k_poisson_f<2, 2, 0>(a); break;
+      default: k_poisson_f<2, 2, 1>(a); break;
+    }
+  });
 }
 
 }  // extern "C"

@@ -245,3 +245,26 @@ def test_cell_parallel_kernels_of_the_small_levels(n):
     ref_r = np.concatenate([O.restrict_u(r4[0]).ravel(), O.restrict_v(r4[1]).ravel(), O.restrict_u(r4[2]).ravel(),
                             O.restrict_v(r4[3]).ravel()])
     assert relerr(emu.cell(3, n, prm, theta, x=x, b=b), ref_r) < 1e-13
+
+
+@pytest.mark.parametrize("n,analytic,rs", [(8, True, 4), (12, False, 2), (32, True, 4), (36, False, 6), (64, True, 8)])
+def test_fused_pressure_poisson_kernels(n, analytic, rs):
+    """csrc/poisson.cuh: pre-smoothing pair, residual + 4-cell-average restriction, piecewise-constant prolongation +
+    sweep (with and without the Chebyshev epilogue), against compositions of the oracle's GtG operator and transfers."""
+    theta, ops, prm = _setup(n, analytic)
+    rng = np.random.default_rng(n + rs)
+    N = n * n
+    p, b = rng.standard_normal(N), rng.standard_normal(N)
+    dg = ops.GtG.diagonal()
+    sweep = lambda v: v + 0.8 * (b - ops.GtG @ v) / dg
+    assert relerr(emu.poisson_f(1, n, prm, theta, b=b, wd=1.0 / dg, rs=rs), sweep(0.8 * b / dg)) < 1e-13
+    ref_r = O.restrict_cell((b - ops.GtG @ p).reshape(n, n)).ravel()
+    assert relerr(emu.poisson_f(3, n, prm, theta, x=p, b=b, rs=rs), ref_r) < 1e-13
+    ec = rng.standard_normal(N // 4)
+    pt = p + O.prolong_cell(ec.reshape(n // 2, n // 2)).ravel()
+    assert relerr(emu.poisson_f(2, n, prm, theta, x=p, b=b, ec=ec, rs=rs), sweep(pt)) < 1e-13
+    d0, xk0 = rng.standard_normal(N), rng.standard_normal(N)
+    d1, xk1 = emu.poisson_f(4, n, prm, theta, x=p, b=b, ec=ec, d=d0, xk=xk0, cheb=(0.3, 1.7), rs=rs)
+    assert relerr(d1, 0.3 * d0 + 1.7 * sweep(pt)) < 1e-13 and relerr(xk1, xk0 + 0.3 * d0 + 1.7 * sweep(pt)) < 1e-13
+    d1, xk1 = emu.poisson_f(4, n, prm, theta, x=p, b=b, ec=ec, d=d0, xk=xk0, cheb=(0.0, 1.7), flags=(0, 0, 1), rs=rs)
+    assert relerr(d1, 1.7 * sweep(pt)) < 1e-13 and relerr(xk1, 1.7 * sweep(pt)) < 1e-13

@@ -378,11 +378,12 @@ def test_fused_mgs_and_graph_replay_are_bitwise_neutral(mp, monkeypatch):
     assert np.array_equal(a[3], b[3]) and np.array_equal(a[2], b[2])
 
 
-@pytest.mark.parametrize("fuse", ["1", "2", "3"])
+@pytest.mark.parametrize("fuse", ["1", "2", "3", "4", "8", "0"])
 @pytest.mark.parametrize("n,eta_n", [(64, 1e3), (48, 10.0), (16, 100.0)])
 def test_fused_smoothing_kernels_vs_oracle(mp, monkeypatch, fuse, n, eta_n):
     """MPBP_FUSE bit 0: the two pre-smoothing sweeps in one kernel; bit 1: prolongation + first post-sweep in
-    one kernel.  Same V-cycle, so the oracle tolerances of the unfused path apply."""
+    one kernel; bit 2: residual + restriction; bit 3: the same three fusions on the pressure-Poisson cycle
+    (csrc/poisson.cuh); default 15.  Same V-cycles, so the oracle tolerances of the unfused path (0) apply."""
     monkeypatch.setenv("MPBP_FUSE", fuse)
     xi, eta_s, c, d = 1.0, 1.0, 1.0, -1.0
     sub = mp.SubSolver(kind="mg", F_cycles=3, P_cycles=2, cheb=True)
@@ -396,11 +397,31 @@ def test_fused_smoothing_kernels_vs_oracle(mp, monkeypatch, fuse, n, eta_n):
     v[4 * N:] -= v[4 * N:].mean()
     mg1 = O.Multigrid(ops, O.SubSolverConfig(kind="mg", cycles=1))
     assert relerr(p.call("mpbp_vcycle_F", v[:4 * N], 4 * N, 4 * N), mg1._vcycle("F", 0, v[:4 * N])) < 1e-10
+    assert relerr(p.call("mpbp_vcycle_P", v[4 * N:], N, N), mg1._vcycle("P", 0, v[4 * N:])) < 1e-10
     Mo = O.ApproxSchur(ops, O.SubSolverConfig(kind="mg", cycles=3, cheb=True))
     cfgP = O.SubSolverConfig(kind="mg", cycles=2, cheb=True)
     Mo.P_inv = O.SubSolver(ops, "P", cfgP, O.Multigrid(ops, cfgP))
     M = bp.approx_schur_operator(c, d)
     assert relerr(M @ v, Mo.matvec(v)) < 1e-9
+
+
+def test_fused_pressure_cycle_is_bitwise_the_unfused_one(mp, monkeypatch):
+    """MPBP_FUSE bit 3 (csrc/poisson.cuh): the fused pressure-Poisson kernels perform the arithmetic of the passes they
+    replace in the same order (1/diag is stored exactly as the sweeps compute it), so the V-cycle and the configured
+    (GtG)~^-1 do not change by a bit."""
+    n = 96
+    rng = np.random.default_rng(9)
+    v = rng.standard_normal(n * n)
+    v -= v.mean()
+    out = {}
+    for fuse in ("7", "15"):
+        monkeypatch.setenv("MPBP_FUSE", fuse)
+        bp = mp.MultiphaseBlockPreconditioner(n, 1.0, 1e3, 1.0, sub_solver=mp.SubSolver(kind="mg", F_cycles=2, P_cycles=3, cheb=True))
+        p = bp.plan(1.0, -1.0)
+        monkeypatch.delenv("MPBP_FUSE")
+        GtG, GtFG, Finv, Pinv = bp.derived_operators(1.0, -1.0)
+        out[fuse] = (p.call("mpbp_vcycle_P", v, n * n, n * n), Pinv @ v)
+    assert np.array_equal(out["7"][0], out["15"][0]) and np.array_equal(out["7"][1], out["15"][1])
 
 
 @pytest.mark.parametrize("cell", ["0", "64", "512"])
