@@ -8,7 +8,8 @@
 //   IN 0, MODE 1, EP 2  residual + 4-cell-average restriction in registers               26N instead of 32N + 10N
 //   IN 2, MODE 2        piecewise-constant prolongation x + P e_c applied while loading + first post-sweep
 //                       (EP 1: ... which is also the last one: Chebyshev epilogue)       34N instead of 18N + 32N
-// Every variant performs exactly the arithmetic of the passes it replaces: the fused cycle is bitwise the unfused one.
+// Every variant performs the arithmetic of the passes it replaces in the same order (bit-identical on the CPU shim; on
+// the device nvcc contracts multiply-adds per instantiation, so fused and unfused cycles agree to rounding).
 // Thread mapping as in stencil.cuh (column marching: a lane owns a column, 3-row window, shuffles for the neighbours).
 #pragma once
 #include "stencil.cuh"

@@ -405,10 +405,11 @@ def test_fused_smoothing_kernels_vs_oracle(mp, monkeypatch, fuse, n, eta_n):
     assert relerr(M @ v, Mo.matvec(v)) < 1e-9
 
 
-def test_fused_pressure_cycle_is_bitwise_the_unfused_one(mp, monkeypatch):
+def test_fused_pressure_cycle_matches_the_unfused_one_to_rounding(mp, monkeypatch):
     """MPBP_FUSE bit 3 (csrc/poisson.cuh): the fused pressure-Poisson kernels perform the arithmetic of the passes they
-    replace in the same order (1/diag is stored exactly as the sweeps compute it), so the V-cycle and the configured
-    (GtG)~^-1 do not change by a bit."""
+    replace in the same order (1/diag is stored exactly as the sweeps compute it; bit-identical on the CPU shim).  On the
+    device nvcc contracts multiply-adds per instantiation, so the V-cycle and the configured (GtG)~^-1 agree to
+    rounding (1e-13 of the result's scale), not bit for bit."""
     n = 96
     rng = np.random.default_rng(9)
     v = rng.standard_normal(n * n)
@@ -421,7 +422,7 @@ def test_fused_pressure_cycle_is_bitwise_the_unfused_one(mp, monkeypatch):
         monkeypatch.delenv("MPBP_FUSE")
         GtG, GtFG, Finv, Pinv = bp.derived_operators(1.0, -1.0)
         out[fuse] = (p.call("mpbp_vcycle_P", v, n * n, n * n), Pinv @ v)
-    assert np.array_equal(out["7"][0], out["15"][0]) and np.array_equal(out["7"][1], out["15"][1])
+    assert relerr(out["15"][0], out["7"][0]) < 1e-13 and relerr(out["15"][1], out["7"][1]) < 1e-13
 
 
 @pytest.mark.parametrize("cell", ["0", "64", "512"])
