@@ -392,10 +392,10 @@ __global__ void __launch_bounds__(kBlockThreads) k_jacobi0_F(const double* __res
 // ------------------------------------------------------------------------------------------
 //   CHEB (MODE 2): the sweep's result z goes through the Chebyshev epilogue (ChebEp) instead of being stored
 //   PUSH: the result's first / last rows also go to the ring neighbours (see PushOut)
-//   (the plain variants are capped at 32 registers, i.e. 16 resident blocks per SM: these kernels consume their loads in
-//   the iteration that issues them and live off occupancy)
+//   (register caps: 32 for the plain variants = 16 resident blocks per SM, 48 / 56 / 64 with the Chebyshev epilogue /
+//   the fused push / both: these kernels consume their loads in the iteration that issues them and live off occupancy)
 template <int MODE, bool CHEB = false, bool PUSH = false>
-__global__ void __launch_bounds__(kBlockThreads, (CHEB || PUSH) ? 1 : 16) k_poisson(VecIn pin, const double* __restrict__ th,
+__global__ void __launch_bounds__(kBlockThreads, (CHEB && PUSH) ? 8 : (PUSH ? 9 : (CHEB ? 10 : 16))) k_poisson(VecIn pin, const double* __restrict__ th,
                                                            const double* __restrict__ b, double* __restrict__ y,
                                                            Geo g, Phys ph, double omega, ChebEp ce = ChebEp{},
                                                            PushOut po = PushOut{}) {
