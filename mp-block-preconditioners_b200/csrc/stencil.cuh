@@ -94,20 +94,9 @@ __device__ __forceinline__ void halo_fetch_cols(double* land, char* comm, size_t
     if (need_bot) land[e + 5 * n] = WARP ? ll_wait_warp(ll_bot + e, s) : ll_wait(ll_bot + e, s);
   }
 }
-#ifdef MPBP_EMU
-#define MPBP_NOINLINE
-#else
-#define MPBP_NOINLINE __noinline__
-#endif
-// out-of-line copy for the light kernels (k_poisson, k_div, k_grad: 32 registers, 16 blocks/SM -- the inlined polling
-// loop cost k_poisson<2> eight registers and a quarter of its occupancy)
-__device__ MPBP_NOINLINE void halo_fetch_warp_noinline(double* land, char* comm, size_t area, const unsigned long long* dseq,
-                                                       int nk, int n, int col, bool need_top, bool need_bot) {
-  halo_fetch_cols<true>(land, comm, area, dseq, 0, nk, 1, n, col, need_top, need_bot);
-}
-__device__ __forceinline__ void halo_fetch_light(const VecIn& v, int nk, int n, int col, bool need_top, bool need_bot) {
-  if (v.dseq != nullptr) halo_fetch_warp_noinline(v.land, v.comm, v.area, v.dseq, nk, n, col, need_top, need_bot);
-}
+// the light kernels (k_poisson, k_div, k_grad: 32 registers, 16 blocks/SM) fetch one or four fields of their own column.
+// Inlined on purpose: an out-of-line call in a kernel takes its loop off the uniform datapath (measured on k_poisson<2>:
+// 18 constant-bank loads per iteration instead of uniform registers, 130 instead of 105 us at 4096^2).
 template <bool WARP = false>
 __device__ __forceinline__ void halo_fetch(const VecIn& v, int k0, int nk, int kstep, int n, int col, bool need_top,
                                            bool need_bot) {
@@ -394,19 +383,22 @@ __global__ void __launch_bounds__(kBlockThreads) k_jacobi0_F(const double* __res
 //   PUSH: the result's first / last rows also go to the ring neighbours (see PushOut)
 //   (register caps: 32 for the plain variants = 16 resident blocks per SM, 48 / 56 / 64 with the Chebyshev epilogue /
 //   the fused push / both: these kernels consume their loads in the iteration that issues them and live off occupancy)
-template <int MODE, bool CHEB = false, bool PUSH = false>
-__global__ void __launch_bounds__(kBlockThreads, (CHEB && PUSH) ? 8 : (PUSH ? 9 : (CHEB ? 10 : 16))) k_poisson(VecIn pin, const double* __restrict__ th,
-                                                           const double* __restrict__ b, double* __restrict__ y,
-                                                           Geo g, Phys ph, double omega, ChebEp ce = ChebEp{},
-                                                           PushOut po = PushOut{}) {
-  const LaneGeom lg = lane_geom(g.n);
-  if (!lg.alive) return;
+template <int MODE, bool CHEB, bool PUSH, bool FETCH>
+__device__ __forceinline__ void poisson_march(const VecIn& pin_, const double* __restrict__ th,
+                                              const double* __restrict__ b, double* __restrict__ y, const Geo& g,
+                                              const Phys& ph, double omega, const ChebEp& ce, const PushOut& po,
+                                              const LaneGeom& lg, int r0, int r1) {
   const int n = g.n, rows = g.rows, c = lg.cc;
-  int r0, r1;
-  if (!strip_rows(g, r0, r1)) return;
-  if (MODE != 3 && (r0 == 0 || r1 == rows)) {
-    halo_fetch_light(pin, 1, n, c, r0 == 0, r1 == rows);
+  // A local copy of the view whose halo pointers are (re)assigned under a uniform condition -- semantically a no-op
+  // (make_view already points top/bot at the landing buffer) but it makes the compiler keep the view in uniform registers:
+  // reading it straight from the parameter bank cost the loop 16 constant loads per iteration and, under the 32-register
+  // cap, spills (k_poisson<2> at 4096^2: 130 us instead of 105).
+  VecIn pin = pin_;
+  if (pin.dseq != nullptr) {
+    pin.top = pin.land;
+    pin.bot = pin.land + (size_t)5 * n;
   }
+  if (FETCH) halo_fetch<true>(pin, 0, 1, 1, n, c, r0 == 0, r1 == rows);
   PushCtx pc{};
   if (PUSH) pc = push_begin(po, r0 == 0, r1 == rows);
   double th_m = th_row(th, r0 - 1, n)[c];
@@ -458,6 +450,22 @@ __global__ void __launch_bounds__(kBlockThreads, (CHEB && PUSH) ? 8 : (PUSH ? 9 
   }
   if (PUSH) push_end(po, pc, r0 == 0, r1 == rows, gridDim.x, gridDim.x, gridDim.y == 1);
 }
+// FETCH (slab edge strips of a distributed level) is a separate instantiation: the polling code in front of the loop
+// takes it off the uniform datapath (18 constant-bank loads per iteration), which the interior strips and every
+// single-GPU launch must not pay for.
+template <int MODE, bool CHEB = false, bool PUSH = false>
+__global__ void __launch_bounds__(kBlockThreads, (CHEB && PUSH) ? 8 : (PUSH ? 9 : (CHEB ? 10 : 16)))
+k_poisson(VecIn pin, const double* __restrict__ th, const double* __restrict__ b, double* __restrict__ y, Geo g, Phys ph,
+          double omega, ChebEp ce = ChebEp{}, PushOut po = PushOut{}) {
+  const LaneGeom lg = lane_geom(g.n);
+  if (!lg.alive) return;
+  int r0, r1;
+  if (!strip_rows(g, r0, r1)) return;
+  if (MODE != 3 && pin.dseq != nullptr && (r0 == 0 || r1 == g.rows))
+    poisson_march<MODE, CHEB, PUSH, true>(pin, th, b, y, g, ph, omega, ce, po, lg, r0, r1);
+  else
+    poisson_march<MODE, CHEB, PUSH, false>(pin, th, b, y, g, ph, omega, ce, po, lg, r0, r1);
+}
 
 // r = D w (+ add): un-negated divergence of both phases (preconditioner.py:221-238, :311; solve.py:259)
 __global__ void __launch_bounds__(kBlockThreads) k_div(VecIn win, const double* __restrict__ th,
@@ -469,7 +477,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_div(VecIn win, const double* 
   int r0, r1;
   if (!strip_rows(g, r0, r1)) return;
   if (r0 == 0 || r1 == rows) {
-    halo_fetch_light(win, 4, n, c, r0 == 0, r1 == rows);
+    halo_fetch<true>(win, 0, 4, 1, n, c, r0 == 0, r1 == rows);
   }
   double th_m = th_row(th, r0 - 1, n)[c];
   double th_c = th_row(th, r0, n)[c];
@@ -504,7 +512,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_grad(VecIn pin, const double*
   int r0, r1;
   if (!strip_rows(g, r0, r1)) return;
   if (r0 == 0 || r1 == rows) {
-    halo_fetch_light(pin, 1, n, c, r0 == 0, r1 == rows);
+    halo_fetch<true>(pin, 0, 1, 1, n, c, r0 == 0, r1 == rows);
   }
   PushCtx pc{};
   if (PUSH) pc = push_begin(po, r0 == 0, r1 == rows);
