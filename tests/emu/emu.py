@@ -202,3 +202,14 @@ def poisson_f(IN, n, prm, theta, x=None, b=None, wd=None, ec=None, d=None, xk=No
     load().emu_poisson_f(IN, n, _p(prm), _p(thp), _p(x), _p(b), _p(wd), _p(ec), _p(d), _p(xk), _p(ch), fl, _p(out), rs,
                          C.c_double(omega))
     return (d, xk) if IN == 4 else out
+
+
+def slab_push_chain_skewed(P, n, prm, theta, x0, b, sweeps=5, rs=4, omega=0.8, seed=1):
+    """LL halo protocol under skew: P free-running emulated ranks (one host thread each, random delays between their
+    kernels) run `sweeps` fused-push Jacobi sweeps and a residual.  Returns the assembled residual."""
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    out = np.zeros_like(b)
+    th = np.ascontiguousarray(theta, dtype=np.float64)
+    load().emu_slab_push_chain_skewed(P, n, _p(prm), _p(th), _p(x0), _p(b), _p(out), rs, C.c_double(omega), sweeps, seed)
+    return out

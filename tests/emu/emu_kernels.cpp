@@ -1,6 +1,7 @@
 // Host build of the CUDA stencil kernels on the SIMT-on-CPU shim (tests/emu/cuda_emu.h): logic checks of
 // the kernels against the oracle on the GPU-less build container.  TEST INFRASTRUCTURE ONLY.
 #define MPBP_EMU 1
+#include <chrono>
 #include "../../mp-block-preconditioners_b200/csrc/stencil.cuh"
 #include "../../mp-block-preconditioners_b200/csrc/coarse.cuh"
 #include "../../mp-block-preconditioners_b200/csrc/stokes.cuh"
@@ -563,6 +564,71 @@ void emu_poisson_f(int in, int n, const double* prm, const double* th_pad, const
       default: k_poisson_f<2, 2, 1>(a); break;
     }
   });
+}
+
+// Stress test of the LL halo protocol under SKEW (slot reuse with >= 3 ranks): every emulated rank runs its
+// whole kernel sequence -- k_halo_push(x0), `sweeps` Jacobi sweeps with fused pushes, a final residual -- in its own
+// host thread, free-running, with pseudo-random delays of up to a few milliseconds between its kernels.  Nothing but
+// the protocol (sequence tags, three slots, producer credit) keeps a fast rank from overwriting rows a slow neighbour
+// has not read yet.  out receives the assembled residual b - F x_sweeps.
+void emu_slab_push_chain_skewed(int P, int n, const double* prm, const double* theta, const double* x0, const double* b,
+                                double* out, int rs, double omega, int sweeps, unsigned seed) {
+  const int rows = n / P;
+  const size_t fs = (size_t)rows * n, area = (size_t)5 * n;
+  std::vector<std::vector<char>> comm(P, std::vector<char>(comm_halo_bytes(area), 0));
+  std::vector<unsigned long long> dseq(P, 0ull);
+  std::vector<std::vector<unsigned int>> counter(P, std::vector<unsigned int>(8, 0u));
+  std::vector<std::vector<double>> xa(P, std::vector<double>(4 * fs)), xb(P, std::vector<double>(4 * fs)),
+      bs(P, std::vector<double>(4 * fs)), thp(P), land(P, std::vector<double>(2 * 5 * n, 0.0));
+  std::vector<Tables> tabs(P);
+  std::vector<Phys> phys(P);
+  for (int g = 0; g < P; ++g) {
+    for (int k = 0; k < 4; ++k) {
+      std::memcpy(&xa[g][k * fs], x0 + (size_t)k * n * n + (size_t)g * rows * n, fs * sizeof(double));
+      std::memcpy(&bs[g][k * fs], b + (size_t)k * n * n + (size_t)g * rows * n, fs * sizeof(double));
+    }
+    thp[g].resize((size_t)(rows + 2) * n);
+    for (int r = -1; r <= rows; ++r)
+      std::memcpy(&thp[g][(size_t)(r + 1) * n], theta + (size_t)(((g * rows + r) % n + n) % n) * n, n * sizeof(double));
+    phys[g] = make_phys(n, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], prm[6], 1, tabs[g]);
+  }
+  const dim3 grid((n + kWarpCols * kBlockWarps - 1) / (kWarpCols * kBlockWarps), (rows + rs - 1) / rs);
+  std::vector<std::thread> ranks;
+  for (int g = 0; g < P; ++g)
+    ranks.emplace_back([&, g] {
+      unsigned state = seed * 2654435761u + 97u * (unsigned)g + 1u;
+      auto nap = [&] {
+        state = state * 1664525u + 1013904223u;
+        std::this_thread::sleep_for(std::chrono::microseconds((state >> 16) % 3000));
+      };
+      const int prev = (g + P - 1) % P, next = (g + 1) % P;
+      nap();
+      emu::launch(dim3((4 * n + 255) / 256), dim3(256), [&] {
+        k_halo_push(xa[g].data(), 4, fs, rows, n, comm[prev].data(), comm[next].data(), comm[g].data(), area, &dseq[g],
+                    &counter[g][0]);
+      });
+      double* src = xa[g].data();
+      double* dst = xb[g].data();
+      for (int step = 0; step <= sweeps; ++step) {
+        nap();
+        StokesArgs a{};
+        a.xin.x = src; a.xin.fs = fs; a.xin.hs = n; a.xin.dseq = &dseq[g]; a.xin.comm = comm[g].data(); a.xin.area = area;
+        a.xin.land = land[g].data(); a.xin.top = a.xin.land; a.xin.bot = a.xin.land + 5 * n;
+        a.th = thp[g].data(); a.b = bs[g].data(); a.y = dst; a.g = Geo{n, rows, g * rows, rs, 3}; a.ph = phys[g];
+        a.omega = omega;
+        a.po = PushOut{comm[prev].data(), comm[next].data(), comm[g].data(), area, &dseq[g], &counter[g][4]};
+        const bool last = step == sweeps;
+        emu::launch(grid, dim3(kBlockThreads), [&] {
+          if (!last) k_stokes_x<0, 2, false, 0, true, 0>(a);
+          else k_stokes_x<0, 1, false, 0, false, 0>(a);
+        });
+        std::swap(src, dst);
+      }
+      // after the swap `src` holds the residual
+      for (int k = 0; k < 4; ++k)
+        std::memcpy(out + (size_t)k * n * n + (size_t)g * rows * n, src + k * fs, fs * sizeof(double));
+    });
+  for (auto& t : ranks) t.join();
 }
 
 }  // extern "C"

@@ -204,6 +204,7 @@ def test_fused_vcycle_kernels_on_distributed_levels(P, n, rs):
     assert relerr(got_x, sweep(sweep(xt))) < 1e-12
 
 
+@pytest.mark.timeout(180)
 @pytest.mark.parametrize("P,n,rs", [(2, 16, 4), (4, 16, 4), (2, 32, 8), (4, 32, 4), (3, 24, 4), (1, 16, 4)])
 def test_fused_residual_restriction_on_slabs(P, n, rs):
     """EP 2 with PUSH (distributed levels): the residual is restricted in registers; a slab's first coarse row is
@@ -268,3 +269,23 @@ def test_fused_pressure_poisson_kernels(n, analytic, rs):
     assert relerr(d1, 0.3 * d0 + 1.7 * sweep(pt)) < 1e-13 and relerr(xk1, xk0 + 0.3 * d0 + 1.7 * sweep(pt)) < 1e-13
     d1, xk1 = emu.poisson_f(4, n, prm, theta, x=p, b=b, ec=ec, d=d0, xk=xk0, cheb=(0.0, 1.7), flags=(0, 0, 1), rs=rs)
     assert relerr(d1, 1.7 * sweep(pt)) < 1e-13 and relerr(xk1, 1.7 * sweep(pt)) < 1e-13
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("P,seed", [(3, 1), (4, 2), (4, 3), (2, 4)])
+def test_ll_halo_protocol_under_rank_skew(P, seed):
+    """Slot reuse of the LL halo protocol with free-running ranks (>= 3 ranks, skew between push and consumer):
+    every emulated rank runs seven exchanging kernels in its own thread with random delays; only the sequence tags, the
+    three slots and the producer credit order them.  A protocol error shows up as wrong rows or as a hang (timeout)."""
+    n = 24 if P == 3 else 16
+    theta, ops, prm = _setup(n, True)
+    rng = np.random.default_rng(seed)
+    x, b = rng.standard_normal(4 * n * n), rng.standard_normal(4 * n * n)
+    dg = ops.F.diagonal()
+    for _ in range(6):
+        x_next = x + 0.8 * (b - ops.F @ x) / dg
+        if _ == 0:
+            x0 = x
+        x = x_next
+    got = emu.slab_push_chain_skewed(P, n, prm, theta, x0, b, sweeps=6, rs=4, seed=seed)
+    assert relerr(got, b - ops.F @ x) < 1e-11
