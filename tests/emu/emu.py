@@ -213,3 +213,13 @@ def slab_push_chain_skewed(P, n, prm, theta, x0, b, sweeps=5, rs=4, omega=0.8, s
     th = np.ascontiguousarray(theta, dtype=np.float64)
     load().emu_slab_push_chain_skewed(P, n, _p(prm), _p(th), _p(x0), _p(b), _p(out), rs, C.c_double(omega), sweeps, seed)
     return out
+
+
+def slab_poisson_chain(P, n, prm, theta, p0, b, sweeps=4, rs=4, omega=0.8, seed=1):
+    """k_poisson on P free-running emulated slabs: push, `sweeps` fused-push GtG sweeps, residual."""
+    p0 = np.ascontiguousarray(p0, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    out = np.zeros_like(b)
+    th = np.ascontiguousarray(theta, dtype=np.float64)
+    load().emu_slab_poisson_chain(P, n, _p(prm), _p(th), _p(p0), _p(b), _p(out), rs, C.c_double(omega), sweeps, seed)
+    return out

@@ -631,4 +631,62 @@ void emu_slab_push_chain_skewed(int P, int n, const double* prm, const double* t
   for (auto& t : ranks) t.join();
 }
 
+// The pressure-Poisson kernels on the slabs of a distributed level, P free-running emulated ranks (one host thread each,
+// random delays): k_halo_push(p0), `sweeps` GtG Jacobi sweeps with fused pushes (k_poisson<2, false, true>: edge strips
+// fetch the neighbours' rows -- the FETCH instantiation -- and push their own), then the residual k_poisson<1>.
+void emu_slab_poisson_chain(int P, int n, const double* prm, const double* theta, const double* p0, const double* b,
+                            double* out, int rs, double omega, int sweeps, unsigned seed) {
+  const int rows = n / P;
+  const size_t fs = (size_t)rows * n, area = (size_t)5 * n;
+  std::vector<std::vector<char>> comm(P, std::vector<char>(comm_halo_bytes(area), 0));
+  std::vector<unsigned long long> dseq(P, 0ull);
+  std::vector<std::vector<unsigned int>> counter(P, std::vector<unsigned int>(8, 0u));
+  std::vector<std::vector<double>> xa(P, std::vector<double>(fs)), xb(P, std::vector<double>(fs)), bs(P, std::vector<double>(fs)),
+      thp(P), land(P, std::vector<double>(2 * 5 * n, 0.0));
+  std::vector<Tables> tabs(P);
+  std::vector<Phys> phys(P);
+  for (int g = 0; g < P; ++g) {
+    std::memcpy(xa[g].data(), p0 + (size_t)g * rows * n, fs * sizeof(double));
+    std::memcpy(bs[g].data(), b + (size_t)g * rows * n, fs * sizeof(double));
+    thp[g].resize((size_t)(rows + 2) * n);
+    for (int r = -1; r <= rows; ++r)
+      std::memcpy(&thp[g][(size_t)(r + 1) * n], theta + (size_t)(((g * rows + r) % n + n) % n) * n, n * sizeof(double));
+    phys[g] = make_phys(n, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], prm[6], 0, tabs[g]);
+  }
+  const dim3 grid((n + kWarpCols * kBlockWarps - 1) / (kWarpCols * kBlockWarps), (rows + rs - 1) / rs);
+  std::vector<std::thread> ranks;
+  for (int g = 0; g < P; ++g)
+    ranks.emplace_back([&, g] {
+      unsigned state = seed * 2654435761u + 131u * (unsigned)g + 7u;
+      auto nap = [&] {
+        state = state * 1664525u + 1013904223u;
+        std::this_thread::sleep_for(std::chrono::microseconds((state >> 16) % 2000));
+      };
+      const int prev = (g + P - 1) % P, next = (g + 1) % P;
+      nap();
+      emu::launch(dim3((n + 255) / 256), dim3(256), [&] {
+        k_halo_push(xa[g].data(), 1, fs, rows, n, comm[prev].data(), comm[next].data(), comm[g].data(), area, &dseq[g],
+                    &counter[g][0]);
+      });
+      double* src = xa[g].data();
+      double* dst = xb[g].data();
+      for (int step = 0; step <= sweeps; ++step) {
+        nap();
+        VecIn in{};
+        in.x = src; in.fs = fs; in.hs = n; in.dseq = &dseq[g]; in.comm = comm[g].data(); in.area = area;
+        in.land = land[g].data(); in.top = in.land; in.bot = in.land + 5 * n;
+        const Geo geo{n, rows, g * rows, rs, 0};
+        const PushOut po{comm[prev].data(), comm[next].data(), comm[g].data(), area, &dseq[g], &counter[g][4]};
+        const bool last = step == sweeps;
+        emu::launch(grid, dim3(kBlockThreads), [&] {
+          if (!last) k_poisson<2, false, true>(in, thp[g].data(), bs[g].data(), dst, geo, phys[g], omega, ChebEp{}, po);
+          else k_poisson<1>(in, thp[g].data(), bs[g].data(), dst, geo, phys[g], omega);
+        });
+        std::swap(src, dst);
+      }
+      std::memcpy(out + (size_t)g * rows * n, src, fs * sizeof(double));
+    });
+  for (auto& t : ranks) t.join();
+}
+
 }  // extern "C"

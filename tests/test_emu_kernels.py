@@ -289,3 +289,21 @@ def test_ll_halo_protocol_under_rank_skew(P, seed):
         x = x_next
     got = emu.slab_push_chain_skewed(P, n, prm, theta, x0, b, sweeps=6, rs=4, seed=seed)
     assert relerr(got, b - ops.F @ x) < 1e-11
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("P,n,rs,seed", [(2, 16, 4, 1), (4, 16, 4, 2), (3, 24, 2, 3), (2, 32, 16, 4), (4, 32, 4, 5)])
+def test_pressure_kernels_on_slabs_with_fused_pushes(P, n, rs, seed):
+    """k_poisson on distributed levels: edge strips fetch the ring neighbours' rows (a separate instantiation of the
+    march) and push their own; free-running ranks as in the skew test.  rs=16 at n=32, P=2 makes one strip per slab (a
+    block that is both the first and the last strip)."""
+    theta, ops, prm = _setup(n, True)
+    rng = np.random.default_rng(seed)
+    N = n * n
+    p, b = rng.standard_normal(N), rng.standard_normal(N)
+    dg = ops.GtG.diagonal()
+    x = p
+    for _ in range(4):
+        x = x + 0.8 * (b - ops.GtG @ x) / dg
+    got = emu.slab_poisson_chain(P, n, prm, theta, p, b, sweeps=4, rs=rs, seed=seed)
+    assert relerr(got, b - ops.GtG @ x) < 1e-12
