@@ -27,6 +27,11 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     xi, eta_n, eta_s, c, d = 1.0, 100.0, 1.0, 1.0, -1.0
     dmin = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    # third argument "nokrylov": operators, V-cycles and the apply only.  Used for the 256 / dist_min_n = 16 stress
+    # hierarchy, whose small distributed levels consist almost entirely of slab-edge rows (general instantiation of the
+    # marching kernels, other multiply-add contraction): the eight single-GPU variants that build the history envelope
+    # below cannot reproduce that, and the histories are compared on the default hierarchy instead (1024, 0).
+    with_krylov = not (len(sys.argv) > 3 and sys.argv[3] == "nokrylov")
     sub = mp.SubSolver(kind="mg", F_cycles=3, P_cycles=2, cheb=True, dist_min_n=dmin)
     ok = True
 
@@ -127,6 +132,13 @@ def main():
 
     # eta_n = 100: right-preconditioned FGMRES (the left-preconditioned history is ill conditioned at this
     # contrast -- the oracle itself moves by tens of percent under 1-ulp perturbations, tests/golden)
+    if not with_krylov:
+        if rank == 0:
+            print("MGPU_ALL_PASS" if ok else "MGPU_FAILED", flush=True)
+        sys.stdout.flush()
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0 if ok else 1)
     krylov_pair("eta100_", eta_n, A1, M1, Ad, Md, b1, bd, ((SIDE_RIGHT, "fgmres"),))
     # eta_n = 1: both Krylov variants
     bp1b = mp.MultiphaseBlockPreconditioner(n, xi, 1.0, eta_s, sub_solver=sub)
