@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_jacobi0_F(const double* __res
                                                              double omega) {
   const LaneGeom lg = lane_geom(g.n);
   if (!lg.alive) return;
-  const int n = g.n, rows = g.rows, c = lg.cc;
+  const int n = g.n, c = lg.cc;
   int r0, r1;
   if (!strip_rows(g, r0, r1)) return;
   double sxf = 0.0, sxc = 0.0;
