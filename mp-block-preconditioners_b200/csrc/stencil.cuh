@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(256) k_dense_matvec(const double* __restrict__
   if (row >= m) return;
   const double* __restrict__ mr = M + (size_t)row * m;
   double acc = 0.0;
-  if ((m & 63) == 0) {
+  if ((m & 63) == 0 && ((reinterpret_cast<uintptr_t>(M) | reinterpret_cast<uintptr_t>(x)) & 15) == 0) {
     // 16-byte loads, eight of them in flight per lane: the matrix is usually NOT L2-resident (a V-cycle streams
     // gigabytes between two coarse solves), so the kernel is one DRAM latency plus 8 MB / all SMs
     const double2* __restrict__ m2 = reinterpret_cast<const double2*>(mr);
